@@ -1,0 +1,3 @@
+from spline_trajectory_optimization_b200.models.race_track import *  # noqa: F401,F403
+from spline_trajectory_optimization_b200.models import race_track as _impl
+__all__ = [n for n in dir(_impl) if not n.startswith('_')]

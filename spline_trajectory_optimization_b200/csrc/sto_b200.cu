@@ -1,0 +1,519 @@
+// sto_b200.cu -- __global__ wrappers and the extern "C" boundary of libsto_b200.so (see include/sto_b200.h).
+//
+// Build (sm_100a only, no FMA contraction so every operation rounds like the reference's NumPy/Python):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC ...
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "sto_common.cuh"
+#include "sto_eval.cuh"
+#include "sto_fit.cuh"
+#include "sto_qss.cuh"
+#include "sto_qss_memo.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what) {
+    g_err = what;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return STO_ERR_CUDA;
+}
+#define STO_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);   \
+    } while (0)
+
+// 32-thread CTAs until every SM has a few warps: the QSS is latency-bound, so spreading warps over all 148
+// SMs matters more than CTA size; larger batches use fuller CTAs to cut launch/scheduling overhead.
+int pick_block(int B) {
+    if (B <= 148 * 32 * 8) return 32;
+    if (B <= 148 * 64 * 16) return 64;
+    return 128;
+}
+inline int grid_for(int B, int block) { return (B + block - 1) / block; }
+
+// ---- workspace carving ---------------------------------------------------------------------------------
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <class T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+    size_t bytes() const { return (off + 255) & ~size_t(255); }
+};
+
+inline size_t ldof(int B) { return (size_t)((B + 31) & ~31); }  // internal leading dimension
+
+struct FitWork { double *cp, *zx, *zy, *zz; };
+FitWork carve_fit(Carver& c, int M, size_t ld) {
+    FitWork w;
+    w.cp = c.take<double>((size_t)M * ld);
+    w.zx = c.take<double>((size_t)M * ld);
+    w.zy = c.take<double>((size_t)M * ld);
+    w.zz = c.take<double>((size_t)M * ld);
+    return w;
+}
+
+struct QssWork {
+    double *dd, *df, *v, *a;
+    uint8_t *rowflag, *sp_flag;
+    int32_t *sp_ent, *sp_ext, *sp_turn;
+    sto::MemoWork memo;
+    int cap;
+};
+inline int effective_impl(int N, int impl) {
+    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N) ? STO_QSS_MEMO : STO_QSS_PLAIN;
+}
+QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool need_state) {
+    QssWork w{};
+    impl = effective_impl(N, impl);
+    w.cap = 2 * N + 64;
+    if (need_chords) {
+        w.dd = c.take<double>((size_t)N * ld);
+        w.df = c.take<double>((size_t)N * ld);
+    }
+    if (need_state) {
+        w.v = c.take<double>((size_t)N * ld);
+        w.a = c.take<double>((size_t)N * ld);
+    }
+    if (impl == STO_QSS_PLAIN) {
+        w.rowflag = c.take<uint8_t>((size_t)N * ld);
+        w.sp_flag = c.take<uint8_t>((size_t)w.cap * ld);
+        w.sp_ent = c.take<int32_t>((size_t)w.cap * ld);
+        w.sp_ext = c.take<int32_t>((size_t)w.cap * ld);
+        w.sp_turn = c.take<int32_t>((size_t)w.cap * ld);
+    } else {
+        w.memo = sto::carve_memo([&](size_t nbytes) { return (void*)c.take<char>(nbytes); }, N, ld, w.cap);
+    }
+    return w;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------
+__global__ void fit_kernel(sto::FitArgs A) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < A.B) sto::fit_candidate(A, b);
+}
+
+__global__ void eval_kernel(sto::EvalArgs A) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < A.B) sto::eval_candidate(A, b);
+}
+
+__global__ void eval_spline_kernel(sto::SplineEvalArgs A) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < A.N) sto::eval_spline_sample(A, j);
+}
+
+// dd / df from explicit x, y columns (the sto_qss_f64 entry); one thread per (sample, candidate)
+__global__ void chord_kernel(const double* x, const double* y, int N, int B, int ld_in, double* dd, double* df,
+                             int ld) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (b >= B) return;
+    int n = (i + 1 == N) ? 0 : i + 1;
+    double x0 = x[sto::at(i, ld_in, b)], y0 = y[sto::at(i, ld_in, b)];
+    double x1 = x[sto::at(n, ld_in, b)], y1 = y[sto::at(n, ld_in, b)];
+    dd[sto::at(i, ld, b)] = sto::chord_qss(x0, y0, x1, y1);
+    df[sto::at(i, ld, b)] = sto::chord_norm(x0, y0, x1, y1);
+}
+
+template <bool OWNER>
+__global__ void qss_plain_kernel(sto::QssArgs A, const __grid_constant__ sto_vehicle_f64 V) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    sto::qss_plain_candidate<OWNER>(A, V, b < A.B ? b : A.B - 1, b < A.B);
+}
+
+__global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, const __grid_constant__ sto_vehicle_f64 V) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    sto::qss_memo_candidate(A, W, V, b < A.B ? b : A.B - 1, b < A.B);
+}
+
+__global__ void zero_status_kernel(int32_t* s, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) s[b] = 0;
+}
+
+// 32x32 tile transpose through shared memory (+1 padding: conflict-free): dst[c][r] = src[r][c]
+__global__ void transpose_kernel(const double* __restrict__ src, int rows, int cols, int ld_src,
+                                 double* __restrict__ dst, int ld_dst) {
+    __shared__ double tile[32][33];
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int r = r0 + k, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[k][threadIdx.x] = src[(size_t)r * ld_src + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int c = c0 + k, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = tile[threadIdx.x][k];
+    }
+}
+
+__global__ void argmin_kernel(const double* lap, const int32_t* status, int B, double* best_lap,
+                              long long* best_idx) {
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double v = lap[b];
+        if (!(v == v) || (status && status[b] != 0)) continue;
+        if (v < bv || bi < 0) { bv = v; bi = b; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, bv, o);
+        long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int nw = (blockDim.x + 31) >> 5;
+        bv = threadIdx.x < nw ? s_v[threadIdx.x] : INFINITY;
+        bi = threadIdx.x < nw ? s_i[threadIdx.x] : -1;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { *best_lap = (bi >= 0) ? bv : nan(""); *best_idx = bi; }
+    }
+}
+
+int check_vehicle(const sto_vehicle_f64* v) {
+    if (!v) return fail(STO_ERR_INVALID, "vehicle is NULL");
+    if (v->n_acc < 2 || v->n_acc > STO_MAX_BREAKS || v->n_dcc < 2 || v->n_dcc > STO_MAX_BREAKS)
+        return fail(STO_ERR_INVALID, "vehicle table sizes must be in [2, STO_MAX_BREAKS]");
+    return STO_OK;
+}
+
+int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* vehicle, int impl, bool owner,
+               cudaStream_t st) {
+    const int block = pick_block(A.B);
+    const int grid = grid_for(A.B, block);
+    impl = effective_impl(A.N, impl);
+    if (impl == STO_QSS_PLAIN) {
+        if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, *vehicle);
+        else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, *vehicle);
+    } else {
+        qss_memo_kernel<<<grid, block, 0, st>>>(A, w.memo, *vehicle);
+    }
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+int sto_abi_version(void) { return STO_B200_ABI_VERSION; }
+const char* sto_last_error(void) { return g_err.c_str(); }
+
+int sto_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+size_t sto_fit_workspace_bytes(int M, int B) {
+    if (M < 3 || B < 1) return 0;
+    Carver c(nullptr);
+    carve_fit(c, M, ldof(B));
+    return c.bytes();
+}
+
+int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                               const double* normal_y, const double* offsets, const double* px,
+                               const double* py, int M, int B, int ld, double* u, double* cx, double* cy,
+                               int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (M < 3) return fail(STO_ERR_INVALID, "fit needs M >= 3 points (trajectory.py:214)");
+    if (B < 1 || ld < B) return fail(STO_ERR_INVALID, "need B >= 1 and ld >= B");
+    if (!u || !cx || !cy || !work) return fail(STO_ERR_INVALID, "u, cx, cy, work must be non-NULL");
+    const bool frenet = centre_x != nullptr;
+    if (frenet && (!centre_y || !normal_x || !normal_y || !offsets))
+        return fail(STO_ERR_INVALID, "centre/normal/offsets must all be given");
+    if (!frenet && (!px || !py)) return fail(STO_ERR_INVALID, "either centre+normal+offsets or px+py");
+    // the work arrays use the caller's leading dimension
+    Carver c(work);
+    sto::FitArgs A{};
+    A.cp = c.take<double>((size_t)M * ld);
+    A.zx = c.take<double>((size_t)M * ld);
+    A.zy = c.take<double>((size_t)M * ld);
+    A.zz = c.take<double>((size_t)M * ld);
+    if (c.bytes() > work_bytes && (size_t)ld > ldof(B)) return fail(STO_ERR_WORKSPACE, "fit workspace: ld too large");
+    if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "fit workspace too small");
+    A.cenx = centre_x; A.ceny = centre_y; A.nrmx = normal_x; A.nrmy = normal_y; A.off = offsets;
+    A.px = px; A.py = py; A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int block = pick_block(B);
+    fit_kernel<<<grid_for(B, block), block, 0, st>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_sample_f64(const double* u, const double* cx, const double* cy, int M, const double* ts, int N, int B,
+                   int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
+                   double* chord_norm, void* stream) {
+    if (M < 3 || N < 1 || B < 1 || ld < B) return fail(STO_ERR_INVALID, "bad sizes");
+    if (!u || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "u, cx, cy, ts must be non-NULL");
+    sto::EvalArgs A{u, cx, cy, ts, M, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
+    const int block = pick_block(B);
+    eval_kernel<<<grid_for(B, block), block, 0, static_cast<cudaStream_t>(stream)>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_sample_spline_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts,
+                          int N, double* x, double* y, double* yaw, double* radius, void* stream) {
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 1) return fail(STO_ERR_INVALID, "bad spline sizes");
+    if (!t || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "t, cx, cy, ts must be non-NULL");
+    sto::SplineEvalArgs A{t, cx, cy, ts, nt, k, N, x, y, yaw, radius};
+    eval_spline_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+size_t sto_qss_workspace_bytes(int N, int B, int impl) {
+    if (N < 2 || B < 1) return 0;
+    Carver c(nullptr);
+    carve_qss(c, N, ldof(B), impl, true, true);
+    c.take<int32_t>((size_t)N * ldof(B));  // owner, if requested through a narrower ld
+    return c.bytes();
+}
+
+int sto_qss_f64(const double* x, const double* y, const double* radius, const double* sin_bank, int N, int B,
+                int ld, const sto_vehicle_f64* vehicle, int impl, double* lap, double* summary,
+                const sto_profile_out_f64* out, int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (N < 2 || B < 1 || ld < B) return fail(STO_ERR_INVALID, "bad sizes");
+    if (!x || !y || !radius || !lap || !work) return fail(STO_ERR_INVALID, "x, y, radius, lap, work must be non-NULL");
+    if (impl != STO_QSS_PLAIN && impl != STO_QSS_MEMO) return fail(STO_ERR_INVALID, "unknown impl");
+    if (int rc = check_vehicle(vehicle)) return rc;
+    if (impl == STO_QSS_MEMO && out && out->owner)
+        return fail(STO_ERR_INVALID, "ITERATION_FLAG (owner) is only tracked by STO_QSS_PLAIN");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t wld = ldof(B);
+    Carver c(work);
+    QssWork w = carve_qss(c, N, wld, impl, true, true);
+    if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "qss workspace too small");
+    {
+        dim3 g((B + 127) / 128, N);
+        chord_kernel<<<g, 128, 0, st>>>(x, y, N, B, ld, w.dd, w.df, (int)wld);
+        STO_CUDA(cudaGetLastError());
+    }
+    // the kernel works on one leading dimension; radius comes in the caller's, so stage it if they differ
+    const double* Rw = radius;
+    if ((size_t)ld != wld) return fail(STO_ERR_INVALID, "sto_qss_f64 needs ld == round_up(B, 32)");
+    sto::QssArgs A{};
+    A.dd = w.dd; A.df = w.df; A.R = Rw; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = (int)wld; A.cap = w.cap;
+    A.v = (out && out->speed) ? out->speed : w.v;
+    A.a = (out && out->lon_acc) ? out->lon_acc : w.a;
+    A.rowflag = w.rowflag; A.sp_ent = w.sp_ent; A.sp_ext = w.sp_ext; A.sp_turn = w.sp_turn; A.sp_flag = w.sp_flag;
+    A.owner = out ? out->owner : nullptr;
+    A.lat = out ? out->lat_acc : nullptr;
+    A.tseg = out ? out->time : nullptr;
+    A.lap = lap; A.summary = summary; A.status = status;
+    if (status) {
+        zero_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(status, B);
+        STO_CUDA(cudaGetLastError());
+    }
+    return launch_qss(A, w, vehicle, impl, A.owner != nullptr, st);
+}
+
+struct LapWork {
+    double *u, *cx, *cy, *R;
+    FitWork fit;
+    QssWork qss;
+};
+static LapWork carve_lap(Carver& c, int M, int N, size_t ld, int impl) {
+    LapWork w;
+    w.u = c.take<double>((size_t)(M + 1) * ld);
+    w.cx = c.take<double>((size_t)(M + 3) * ld);
+    w.cy = c.take<double>((size_t)(M + 3) * ld);
+    w.R = c.take<double>((size_t)N * ld);
+    w.fit = carve_fit(c, M, ld);
+    w.qss = carve_qss(c, N, ld, impl, true, true);
+    return w;
+}
+
+size_t sto_lap_workspace_bytes(int M, int N, int B, int impl) {
+    if (M < 3 || N < 2 || B < 1) return 0;
+    Carver c(nullptr);
+    carve_lap(c, M, N, ldof(B), impl);
+    return c.bytes();
+}
+
+int sto_lap_time_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                     const double* normal_y, const double* sin_bank, const double* ts, const double* offsets,
+                     int M, int N, int B, int ld, const sto_vehicle_f64* vehicle, int impl, double* lap,
+                     int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (M < 3 || N < 2 || B < 1 || ld < B) return fail(STO_ERR_INVALID, "bad sizes");
+    if (!centre_x || !centre_y || !normal_x || !normal_y || !ts || !offsets || !lap || !status || !work)
+        return fail(STO_ERR_INVALID, "NULL argument");
+    if (impl != STO_QSS_PLAIN && impl != STO_QSS_MEMO) return fail(STO_ERR_INVALID, "unknown impl");
+    if ((size_t)ld != ldof(B)) return fail(STO_ERR_INVALID, "sto_lap_time_f64 needs ld == round_up(B, 32)");
+    if (int rc = check_vehicle(vehicle)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(work);
+    LapWork w = carve_lap(c, M, N, (size_t)ld, impl);
+    if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "lap workspace too small");
+    const int block = pick_block(B), grid = grid_for(B, block);
+    zero_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(status, B);
+    sto::FitArgs F{};
+    F.cenx = centre_x; F.ceny = centre_y; F.nrmx = normal_x; F.nrmy = normal_y; F.off = offsets;
+    F.M = M; F.B = B; F.ld = ld; F.u = w.u; F.cx = w.cx; F.cy = w.cy; F.status = status;
+    F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz;
+    fit_kernel<<<grid, block, 0, st>>>(F);
+    STO_CUDA(cudaGetLastError());
+    // lap-only: x, y, yaw are never materialised; the chords and the radius are all the QSS reads
+    sto::EvalArgs E{w.u, w.cx, w.cy, ts, M, N, B, ld, nullptr, nullptr, nullptr, w.R, w.qss.dd, w.qss.df};
+    eval_kernel<<<grid, block, 0, st>>>(E);
+    STO_CUDA(cudaGetLastError());
+    sto::QssArgs A{};
+    A.dd = w.qss.dd; A.df = w.qss.df; A.R = w.R; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = ld; A.cap = w.qss.cap;
+    A.v = w.qss.v; A.a = w.qss.a; A.rowflag = w.qss.rowflag;
+    A.sp_ent = w.qss.sp_ent; A.sp_ext = w.qss.sp_ext; A.sp_turn = w.qss.sp_turn; A.sp_flag = w.qss.sp_flag;
+    A.lap = lap; A.status = status;
+    return launch_qss(A, w.qss, vehicle, impl, false, st);
+}
+
+int sto_transpose_f64(const double* src, int rows, int cols, int ld_src, double* dst, int ld_dst, void* stream) {
+    if (!src || !dst || rows < 1 || cols < 1 || ld_src < cols || ld_dst < rows)
+        return fail(STO_ERR_INVALID, "bad transpose arguments");
+    dim3 g((cols + 31) / 32, (rows + 31) / 32), blk(32, 8);
+    transpose_kernel<<<g, blk, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, dst, ld_dst);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_argmin_f64(const double* lap, const int32_t* status, int B, double* best_lap, int64_t* best_idx,
+                   void* stream) {
+    if (!lap || !best_lap || !best_idx || B < 1) return fail(STO_ERR_INVALID, "bad argmin arguments");
+    argmin_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(lap, status, B, best_lap,
+                                                                     reinterpret_cast<long long*>(best_idx));
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+// ---- host-buffer entry: the call a ctypes binding makes ---------------------------------------------------
+namespace {
+struct Arena {  // grow-only device arena per device, reused across calls (cudaMalloc is not free)
+    void* p = nullptr;
+    size_t n = 0;
+    int dev = -1;
+};
+std::mutex g_arena_mu;
+Arena g_arena;
+int arena_get(int dev, size_t bytes, void** out) {
+    if (g_arena.dev != dev || g_arena.n < bytes) {
+        if (g_arena.p) { cudaSetDevice(g_arena.dev); cudaFree(g_arena.p); g_arena = Arena{}; cudaSetDevice(dev); }
+        STO_CUDA(cudaMalloc(&g_arena.p, bytes));
+        g_arena.n = bytes;
+        g_arena.dev = dev;
+    }
+    *out = g_arena.p;
+    return STO_OK;
+}
+}  // namespace
+
+int sto_release(void) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (g_arena.p) { cudaSetDevice(g_arena.dev); cudaFree(g_arena.p); g_arena = Arena{}; }
+    return STO_OK;
+}
+
+int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                          const double* normal_y, const double* sin_bank, const double* ts,
+                          const double* offsets_host, int M, int N, int B, const sto_vehicle_f64* vehicle,
+                          int impl, double* lap_host, int32_t* status_host, int device,
+                          size_t max_work_bytes) {
+    if (M < 3 || N < 2 || B < 1) return fail(STO_ERR_INVALID, "bad sizes");
+    if (!centre_x || !centre_y || !normal_x || !normal_y || !ts || !offsets_host || !lap_host || !status_host)
+        return fail(STO_ERR_INVALID, "NULL argument");
+    if (int rc = check_vehicle(vehicle)) return rc;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    STO_CUDA(cudaSetDevice(device));
+    size_t free_b = 0, total_b = 0;
+    STO_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = max_work_bytes ? max_work_bytes : (size_t)32 << 30;
+    size_t avail = free_b + ((g_arena.dev == device) ? g_arena.n : 0);
+    if (budget > avail / 10 * 8) budget = avail / 10 * 8;
+    // chunk size: the largest multiple of 32 candidates whose buffers fit the budget
+    auto need = [&](int bc) {
+        size_t ld = ldof(bc);
+        return sto_lap_workspace_bytes(M, N, bc, impl) + 2 * (size_t)M * ld * sizeof(double)  // staged + transposed
+               + (size_t)(5 * M + 2 * N) * sizeof(double) + ld * (sizeof(double) + sizeof(int32_t)) + 8192;
+    };
+    int bc = B;
+    while (bc > 32 && need(bc) > budget) bc = ((bc / 2) + 31) & ~31;
+    if (need(bc) > budget) return fail(STO_ERR_WORKSPACE, "device memory budget too small for 32 candidates");
+    void* base = nullptr;
+    if (int rc = arena_get(device, need(bc), &base)) return rc;
+    const size_t ld = ldof(bc);
+    Carver c(base);
+    double* d_cx = c.take<double>(M); double* d_cy = c.take<double>(M);
+    double* d_nx = c.take<double>(M); double* d_ny = c.take<double>(M);
+    double* d_sb = c.take<double>(N); double* d_ts = c.take<double>(N);
+    double* d_stage = c.take<double>((size_t)M * ld);  // [bc][M] as the user holds it
+    double* d_off = c.take<double>((size_t)M * ld);    // [M][ld]
+    double* d_lap = c.take<double>(ld);
+    int32_t* d_status = c.take<int32_t>(ld);
+    void* d_work = c.take<char>(sto_lap_workspace_bytes(M, N, bc, impl));
+    const size_t work_bytes = sto_lap_workspace_bytes(M, N, bc, impl);
+    cudaStream_t st = nullptr;
+    STO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = STO_OK;
+    auto H2D = [&](void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st); };
+    cudaError_t e = H2D(d_cx, centre_x, sizeof(double) * M);
+    if (e == cudaSuccess) e = H2D(d_cy, centre_y, sizeof(double) * M);
+    if (e == cudaSuccess) e = H2D(d_nx, normal_x, sizeof(double) * M);
+    if (e == cudaSuccess) e = H2D(d_ny, normal_y, sizeof(double) * M);
+    if (e == cudaSuccess) e = H2D(d_ts, ts, sizeof(double) * N);
+    if (e == cudaSuccess && sin_bank) e = H2D(d_sb, sin_bank, sizeof(double) * N);
+    if (e != cudaSuccess) rc = fail_cuda(e, "H2D of track tables");
+    for (int b0 = 0; rc == STO_OK && b0 < B; b0 += bc) {
+        const int nb = (B - b0 < bc) ? B - b0 : bc;
+        const int nld = (int)ldof(nb);
+        e = H2D(d_stage, offsets_host + (size_t)b0 * M, sizeof(double) * (size_t)nb * M);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "H2D of offsets"); break; }
+        if (nld != nb) {  // padding lanes of the last warp read defined data
+            e = cudaMemsetAsync(d_off, 0, sizeof(double) * (size_t)M * nld, st);
+            if (e != cudaSuccess) { rc = fail_cuda(e, "memset"); break; }
+        }
+        rc = sto_transpose_f64(d_stage, nb, M, M, d_off, nld, st);
+        if (rc) break;
+        rc = sto_lap_time_f64(d_cx, d_cy, d_nx, d_ny, sin_bank ? d_sb : nullptr, d_ts, d_off, M, N, nb, nld, vehicle,
+                              impl, d_lap, d_status, d_work, work_bytes, st);
+        if (rc) break;
+        e = cudaMemcpyAsync(lap_host + b0, d_lap, sizeof(double) * nb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(status_host + b0, d_status, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "D2H of lap times"); break; }
+    }
+    e = cudaStreamSynchronize(st);
+    if (rc == STO_OK && e != cudaSuccess) rc = fail_cuda(e, "stream synchronize");
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

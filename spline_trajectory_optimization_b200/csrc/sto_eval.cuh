@@ -1,0 +1,246 @@
+// sto_eval.cuh -- arc-parameter resampling of a fitted closed cubic B-spline with heading and turn radius.
+//
+// Replaces BSplineTrajectory.sample_along(ts=...) and its helpers __get_yaw / __get_turn_radius
+// (spline_traj_optm/models/trajectory.py:250-260,268-281).  The six evaluations (x, y and their first two
+// derivatives) follow SciPy's evaluate_spline -> _deBoor_D operation order exactly, so that on identical
+// coefficients the samples are bit-identical to scipy.interpolate.splev (a textbook "differentiate the
+// control polygon" evaluator differs by ~4e-6 absolute in the second derivative).
+//
+// One candidate per thread; every candidate has its own knot vector (chord-length parameter of its own
+// points), so the interval search is a per-thread monotone walk that stays within +-1 knot of its warp
+// neighbours (all candidates have u_i ~ i/M): knot / coefficient loads stay coalesced.
+#pragma once
+#include "sto_common.cuh"
+
+namespace sto {
+
+struct EvalArgs {
+    const double *u, *cx, *cy;  // [M+1][ld], [M+3][ld], [M+3][ld]
+    const double* ts;           // [N] shared parameters
+    int M, N, B, ld;
+    double *x, *y, *yaw, *radius, *chord_qss, *chord_norm;  // [N][ld], each optional
+};
+
+// Knot U(i), i in [-3, M+3], from the normalised chord parameter (periodic extension, period 1).
+STO_HD double eval_knot(const EvalArgs& A, int i, int b) {
+    if (i < 0) return A.u[at(A.M + i, A.ld, b)] - 1.0;
+    if (i > A.M) return A.u[at(i - A.M, A.ld, b)] + 1.0;
+    return A.u[at(i, A.ld, b)];
+}
+
+// Cubic basis values and first/second derivative bases at x for the knot window tk[0..5] = t[ell-2..ell+3],
+// transcribing _deBoor_D (k = 3) for m = 0, 1, 2.  The leading "standard" iterations are common to the three
+// derivative orders and are computed once; each is the identical operation sequence SciPy runs.
+STO_HD void cubic_basis_d012(const double* tk, double x, double* h0, double* h1, double* h2) {
+    // t[ell + n] = tk[2 + n],  t[ell + n - j] = tk[2 + n - j]
+    // j = 1 (standard): from h = {1}
+    double a0, a1;
+    {
+        double xb = tk[3], xa = tk[2];
+        double w = 1.0 / (xb - xa);
+        a0 = 0.0 + w * (xb - x);
+        a1 = w * (x - xa);
+    }
+    // m = 2: derivative iterations j = 2, 3 applied to {a0, a1}
+    {
+        double c0, c1, c2;
+        {   // j = 2
+            double w1 = 2 * a0 / (tk[3] - tk[1]);
+            c0 = 0.0 - w1;
+            c1 = w1;
+            double w2 = 2 * a1 / (tk[4] - tk[2]);
+            c1 = c1 - w2;
+            c2 = w2;
+        }
+        {   // j = 3
+            double w1 = 3 * c0 / (tk[3] - tk[0]);
+            double r0 = 0.0 - w1, r1 = w1;
+            double w2 = 3 * c1 / (tk[4] - tk[1]);
+            r1 = r1 - w2;
+            double r2 = w2;
+            double w3 = 3 * c2 / (tk[5] - tk[2]);
+            r2 = r2 - w3;
+            h2[0] = r0; h2[1] = r1; h2[2] = r2; h2[3] = w3;
+        }
+    }
+    // j = 2 (standard): from {a0, a1}
+    double b0, b1, b2;
+    {
+        double w1 = a0 / (tk[3] - tk[1]);
+        b0 = 0.0 + w1 * (tk[3] - x);
+        b1 = w1 * (x - tk[1]);
+        double w2 = a1 / (tk[4] - tk[2]);
+        b1 = b1 + w2 * (tk[4] - x);
+        b2 = w2 * (x - tk[2]);
+    }
+    // m = 1: derivative iteration j = 3 applied to {b0, b1, b2}
+    {
+        double w1 = 3 * b0 / (tk[3] - tk[0]);
+        double r0 = 0.0 - w1, r1 = w1;
+        double w2 = 3 * b1 / (tk[4] - tk[1]);
+        r1 = r1 - w2;
+        double r2 = w2;
+        double w3 = 3 * b2 / (tk[5] - tk[2]);
+        r2 = r2 - w3;
+        h1[0] = r0; h1[1] = r1; h1[2] = r2; h1[3] = w3;
+    }
+    // m = 0: j = 3 (standard)
+    {
+        double w1 = b0 / (tk[3] - tk[0]);
+        double r0 = 0.0 + w1 * (tk[3] - x);
+        double r1 = w1 * (x - tk[0]);
+        double w2 = b1 / (tk[4] - tk[1]);
+        r1 = r1 + w2 * (tk[4] - x);
+        double r2 = w2 * (x - tk[1]);
+        double w3 = b2 / (tk[5] - tk[2]);
+        r2 = r2 + w3 * (tk[5] - x);
+        h0[0] = r0; h0[1] = r1; h0[2] = r2; h0[3] = w3 * (x - tk[2]);
+    }
+}
+
+STO_HD double dot4(const double* c, const double* h) {
+    double acc = 0.0;
+    acc = acc + c[0] * h[0];
+    acc = acc + c[1] * h[1];
+    acc = acc + c[2] * h[2];
+    acc = acc + c[3] * h[3];
+    return acc;
+}
+
+// trajectory.py:253-260: turn radius = 1 / | |x'y'' - y'x''| / sqrt((x'^2 + y'^2)^3) |
+STO_HD double turn_radius(double dx, double dy, double ddx, double ddy) {
+    double num = fabs(dx * ddy - dy * ddx);
+    double s2 = dx * dx + dy * dy;
+    double s6 = (s2 * s2) * s2;
+    double curv = num / sqrt(s6);
+    return 1.0 / fabs(curv);
+}
+
+STO_HD void eval_candidate(const EvalArgs& A, int b) {
+    const int M = A.M, N = A.N, ld = A.ld;
+    int i = 0;  // knot interval: U(i) <= x < U(i+1), clamped to [0, M-1]  (ell = i + 3)
+    int loaded = -1000;
+    double tk[6], ccx[4], ccy[4];
+    double x_first = 0.0, y_first = 0.0, x_prev = 0.0, y_prev = 0.0;
+    const bool want_chord = A.chord_qss || A.chord_norm;
+    for (int j = 0; j < N; ++j) {
+        const double x = A.ts[j];
+        // scipy _find_interval, started from the previous interval
+        while (i > 0 && x < ((loaded == i) ? tk[2] : eval_knot(A, i, b))) { --i; }
+        while (i < M - 1 && x >= ((loaded == i) ? tk[3] : eval_knot(A, i + 1, b))) {
+            ++i;
+            if (loaded == i - 1) {  // slide the register window by one knot
+                tk[0] = tk[1]; tk[1] = tk[2]; tk[2] = tk[3]; tk[3] = tk[4]; tk[4] = tk[5];
+                tk[5] = eval_knot(A, i + 3, b);
+                ccx[0] = ccx[1]; ccx[1] = ccx[2]; ccx[2] = ccx[3]; ccx[3] = A.cx[at(i + 3, ld, b)];
+                ccy[0] = ccy[1]; ccy[1] = ccy[2]; ccy[2] = ccy[3]; ccy[3] = A.cy[at(i + 3, ld, b)];
+                loaded = i;
+            }
+        }
+        if (loaded != i) {
+            for (int n = 0; n < 6; ++n) tk[n] = eval_knot(A, i - 2 + n, b);
+            for (int n = 0; n < 4; ++n) { ccx[n] = A.cx[at(i + n, ld, b)]; ccy[n] = A.cy[at(i + n, ld, b)]; }
+            loaded = i;
+        }
+        double h0[4], h1[4], h2[4];
+        cubic_basis_d012(tk, x, h0, h1, h2);
+        const double px = dot4(ccx, h0), py = dot4(ccy, h0);
+        const double dx = dot4(ccx, h1), dy = dot4(ccy, h1);
+        const double ddx = dot4(ccx, h2), ddy = dot4(ccy, h2);
+        if (A.x) A.x[at(j, ld, b)] = px;
+        if (A.y) A.y[at(j, ld, b)] = py;
+        if (A.yaw) A.yaw[at(j, ld, b)] = atan2(dy, dx);
+        if (A.radius) A.radius[at(j, ld, b)] = turn_radius(dx, dy, ddx, ddy);
+        if (want_chord) {
+            if (j == 0) { x_first = px; y_first = py; }
+            else {
+                if (A.chord_qss) A.chord_qss[at(j - 1, ld, b)] = chord_qss(x_prev, y_prev, px, py);
+                if (A.chord_norm) A.chord_norm[at(j - 1, ld, b)] = chord_norm(x_prev, y_prev, px, py);
+            }
+            x_prev = px; y_prev = py;
+        }
+    }
+    if (want_chord && N > 0) {
+        if (A.chord_qss) A.chord_qss[at(N - 1, ld, b)] = chord_qss(x_prev, y_prev, x_first, y_first);
+        if (A.chord_norm) A.chord_norm[at(N - 1, ld, b)] = chord_norm(x_prev, y_prev, x_first, y_first);
+    }
+}
+
+// ---- generic degree (1..5), shared knots: one thread per SAMPLE ------------------------------------------
+// scipy _deBoor_D verbatim semantics for any k; used for the track's own splines (k = 3 or 5, smoothing fits
+// produced on the host by FITPACK) so their sampling also runs on the device.
+STO_HD void deboor_d(const double* t, double x, int k, int ell, int m, double* h /*k+1*/) {
+    double hh[6];
+    h[0] = 1.0;
+    for (int j = 1; j <= k - m; ++j) {
+        for (int n = 0; n < j; ++n) hh[n] = h[n];
+        h[0] = 0.0;
+        for (int n = 1; n <= j; ++n) {
+            int ind = ell + n;
+            double xb = t[ind], xa = t[ind - j];
+            if (xb == xa) { h[n] = 0.0; continue; }
+            double w = hh[n - 1] / (xb - xa);
+            h[n - 1] += w * (xb - x);
+            h[n] = w * (x - xa);
+        }
+    }
+    for (int j = k - m + 1; j <= k; ++j) {
+        for (int n = 0; n < j; ++n) hh[n] = h[n];
+        h[0] = 0.0;
+        for (int n = 1; n <= j; ++n) {
+            int ind = ell + n;
+            double xb = t[ind], xa = t[ind - j];
+            if (xb == xa) { h[m] = 0.0; continue; }
+            double w = j * hh[n - 1] / (xb - xa);
+            h[n - 1] -= w;
+            h[n] = w;
+        }
+    }
+}
+
+struct SplineEvalArgs {
+    const double *t, *cx, *cy, *ts;
+    int nt, k, N;
+    double *x, *y, *yaw, *radius;
+};
+
+STO_HD void eval_spline_sample(const SplineEvalArgs& A, int j) {
+    const int k = A.k, n = A.nt - k - 1;
+    const double x = A.ts[j];
+    // interval by bisection: t[ell] <= x < t[ell+1], clamped to [k, n-1] (extrapolate=True)
+    int ell;
+    if (!(x == x)) {
+        const double qnan = nan("");
+        if (A.x) A.x[j] = qnan;
+        if (A.y) A.y[j] = qnan;
+        if (A.yaw) A.yaw[j] = qnan;
+        if (A.radius) A.radius[j] = qnan;
+        return;
+    }
+    if (x < A.t[k + 1] || n - 1 == k) ell = k;
+    else if (x >= A.t[n - 1]) ell = n - 1;
+    else {
+        int lo = k, hi = n - 1;  // t[lo] <= x < t[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (x >= A.t[mid]) lo = mid; else hi = mid;
+        }
+        ell = lo;
+    }
+    double h[6], v[6];
+    for (int m = 0; m < 3; ++m) {
+        deboor_d(A.t, x, k, ell, m, h);
+        double ax = 0.0, ay = 0.0;
+        for (int a = 0; a <= k; ++a) {
+            ax = ax + A.cx[ell + a - k] * h[a];
+            ay = ay + A.cy[ell + a - k] * h[a];
+        }
+        v[2 * m] = ax; v[2 * m + 1] = ay;
+    }
+    if (A.x) A.x[j] = v[0];
+    if (A.y) A.y[j] = v[1];
+    if (A.yaw) A.yaw[j] = atan2(v[3], v[2]);
+    if (A.radius) A.radius[j] = turn_radius(v[2], v[3], v[4], v[5]);
+}
+
+}  // namespace sto

@@ -1,0 +1,53 @@
+"""Shared test helpers: golden loading, vehicle construction for oracle / hostsim / product, GPU glue."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SIM_CASES = ["sim_s30k5_i10", "sim_s30k5_i5", "sim_s30k5_i3", "sim_s10k3_i10", "sim_s10k3_i5", "sim_s10k3_i2",
+             "sim_s0k3_i10", "sim_oval_bank12", "sim_oval_bank0", "sim_s10k3_i10_vehicle5"]
+CAND_CASES = ["cand_m579_n579", "cand_m579_n1158", "cand_m2895_n2895"]
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def veh_args(d):
+    return (d["veh_scalars"], d["veh_acc_x"], d["veh_acc_c"], d["veh_dcc_x"], d["veh_dcc_c"])
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    if not fin.any():
+        return 0.0
+    return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)))
+
+
+def test_vehicle_params():
+    from spline_trajectory_optimization_b200.models.vehicle import VehicleParams
+    acc = np.array([[0.0, 10.0], [50.0, 7.0], [100.0, 0.5]])
+    dcc = np.array([[0.0, -13.0], [50.0, -15.0], [100.0, -20.0]])
+    return VehicleParams(acc, dcc, 10.0, -20.0, 15.0, -15.0, 100.0, 30.0)
+
+
+test_vehicle_params.__test__ = False
+
+
+def to_sm(a_cm, device="cuda"):
+    """[B, n] host candidate-major -> [n, round_up(B, 32)] device sample-major (zero padded)."""
+    import torch
+    a = np.asarray(a_cm, dtype=np.float64)
+    B, n = a.shape
+    ld = (B + 31) & ~31
+    out = torch.zeros((n, ld), dtype=torch.float64, device=device)
+    out[:, :B] = torch.from_numpy(np.ascontiguousarray(a.T)).to(device)
+    return out
+
+
+def to_cm(t_sm, B):
+    return t_sm[:, :B].T.contiguous().cpu().numpy()

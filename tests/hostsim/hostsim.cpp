@@ -1,0 +1,82 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the per-candidate device functions of
+// spline_trajectory_optimization_b200/csrc/*.cuh for the host (g++, -ffp-contract=off) so the schedule logic
+// (row tables, ring windows, memoisation) can be unit-tested in the GPU-less authoring container.  Each
+// candidate runs as a "warp of one".  The product never builds, loads or falls back to this file.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../spline_trajectory_optimization_b200/csrc/sto_common.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_eval.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_fit.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_qss.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_qss_memo.cuh"
+
+extern "C" {
+
+int hostsim_fit(const double* cenx, const double* ceny, const double* nrmx, const double* nrmy, const double* off,
+                const double* px, const double* py, int M, int B, int ld, double* u, double* cx, double* cy,
+                int32_t* status) {
+    std::vector<double> w((size_t)4 * M * ld);
+    sto::FitArgs A{};
+    A.cenx = cenx; A.ceny = ceny; A.nrmx = nrmx; A.nrmy = nrmy; A.off = off; A.px = px; A.py = py;
+    A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
+    A.cp = w.data(); A.zx = A.cp + (size_t)M * ld; A.zy = A.zx + (size_t)M * ld; A.zz = A.zy + (size_t)M * ld;
+    for (int b = 0; b < B; ++b) sto::fit_candidate(A, b);
+    return 0;
+}
+
+int hostsim_eval(const double* u, const double* cx, const double* cy, int M, const double* ts, int N, int B, int ld,
+                 double* x, double* y, double* yaw, double* radius, double* chord_qss, double* chord_norm) {
+    sto::EvalArgs A{u, cx, cy, ts, M, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
+    for (int b = 0; b < B; ++b) sto::eval_candidate(A, b);
+    return 0;
+}
+
+int hostsim_eval_spline(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
+                        double* x, double* y, double* yaw, double* radius) {
+    sto::SplineEvalArgs A{t, cx, cy, ts, nt, k, N, x, y, yaw, radius};
+    for (int j = 0; j < N; ++j) sto::eval_spline_sample(A, j);
+    return 0;
+}
+
+// x, y, radius: [N][ld]; outputs v, a, lat, tseg [N][ld], owner [N][ld] (plain only, may be NULL), lap[B],
+// summary[8][ld], status[B]
+int hostsim_qss(int impl, const double* x, const double* y, const double* radius, const double* sinb, int N, int B,
+                int ld, const sto_vehicle_f64* V, double* v, double* a, double* lat, double* tseg, int32_t* owner,
+                double* lap, double* summary, int32_t* status) {
+    const int cap = 2 * N + 64;
+    std::vector<double> dd((size_t)N * ld), df((size_t)N * ld);
+    for (int i = 0; i < N; ++i)
+        for (int b = 0; b < B; ++b) {
+            int n = (i + 1 == N) ? 0 : i + 1;
+            double x0 = x[sto::at(i, ld, b)], y0 = y[sto::at(i, ld, b)], x1 = x[sto::at(n, ld, b)],
+                   y1 = y[sto::at(n, ld, b)];
+            dd[sto::at(i, ld, b)] = sto::chord_qss(x0, y0, x1, y1);
+            df[sto::at(i, ld, b)] = sto::chord_norm(x0, y0, x1, y1);
+        }
+    std::vector<uint8_t> rowflag((size_t)N * ld), spf((size_t)cap * ld);
+    std::vector<int32_t> e1((size_t)cap * ld), e2((size_t)cap * ld), e3((size_t)cap * ld);
+    sto::QssArgs A{};
+    A.dd = dd.data(); A.df = df.data(); A.R = radius; A.sinb = sinb; A.N = N; A.B = B; A.ld = ld; A.cap = cap;
+    A.v = v; A.a = a; A.rowflag = rowflag.data(); A.sp_ent = e1.data(); A.sp_ext = e2.data(); A.sp_turn = e3.data();
+    A.sp_flag = spf.data(); A.owner = owner; A.lat = lat; A.tseg = tseg; A.lap = lap; A.summary = summary;
+    A.status = status;
+    for (int b = 0; b < B; ++b) status[b] = 0;
+    if (impl == STO_QSS_PLAIN || N < 128) {
+        for (int b = 0; b < B; ++b) {
+            if (owner) sto::qss_plain_candidate<true>(A, *V, b, true);
+            else sto::qss_plain_candidate<false>(A, *V, b, true);
+        }
+    } else {
+        std::vector<std::vector<char>> keep;
+        sto::MemoWork W = sto::carve_memo([&](size_t n) { keep.emplace_back(n); return (void*)keep.back().data(); },
+                                          N, (size_t)ld, cap);
+        for (int b = 0; b < B; ++b) sto::qss_memo_candidate(A, W, *V, b, true);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+"""CPU: the per-candidate device functions (csrc/*.cuh) compiled for the host, against the oracle.  Exercises the
+kernel logic (implicit row positions, re-spawned row table, ring windows, edge memoisation) without a GPU.  The
+oracle runs in ref_pow=0 mode (plain products), the arithmetic the kernels use: everything must match BIT FOR BIT."""
+import numpy as np
+import pytest
+
+import hostsim_py as H
+import oracle_py as O
+from helpers import CAND_CASES, SIM_CASES, golden, veh_args
+
+
+@pytest.mark.parametrize("name", CAND_CASES[:2])
+def test_fit_and_eval_bit_exact(name):
+    d = golden(name)
+    u, cx, cy, st = H.fit_points(d["points"])
+    assert not st.any()
+    E = H.evaluate(u, cx, cy, d["ts"])
+    for b in range(d["points"].shape[0]):
+        t, ocx, ocy = O.fit_periodic_cubic(d["points"][b])
+        assert np.array_equal(u[b], t[3:-3]) and np.array_equal(cx[b], ocx) and np.array_equal(cy[b], ocy)
+        X, Y, YAW, R = O.sample(t, ocx, ocy, 3, d["ts"], 0)
+        assert np.array_equal(E["x"][b], X) and np.array_equal(E["y"][b], Y) and np.array_equal(E["radius"][b], R)
+        assert np.max(np.abs(E["yaw"][b] - YAW)) < 1e-15
+
+
+def test_fit_from_offsets_equals_fit_from_points():
+    d = golden("cand_m579_n579")
+    nx, ny = -np.sin(d["centre_yaw"]), np.cos(d["centre_yaw"])
+    u1, cx1, cy1, _ = H.fit_offsets(d["centre_x"], d["centre_y"], nx, ny, d["offsets"])
+    u2, cx2, cy2, _ = H.fit_points(d["points"])
+    assert np.array_equal(u1, u2) and np.array_equal(cx1, cx2) and np.array_equal(cy1, cy2)
+
+
+@pytest.mark.parametrize("name", SIM_CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_qss_both_schedules_bit_exact(name, impl):
+    d = golden(name)
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    sb = np.sin(d["in_BANK"])
+    o = O.qss(d["in_X"], d["in_Y"], d["in_CURVATURE"], sb, ov, 0)
+    r = H.qss(impl, d["in_X"][None], d["in_Y"][None], d["in_CURVATURE"][None], sb, hv, owner=(impl == 0))
+    assert r["status"][0] == 0
+    for k, ok in (("v", "v"), ("a", "a"), ("lat", "lat"), ("time", "time")):
+        assert np.array_equal(r[k][0], o[ok]), k
+    assert r["lap"][0] == o["lap"]
+    assert r["summary"][0, 6] == o["steps"] and r["summary"][0, 7] == o["iters"] + 1
+    if impl == 0:
+        assert np.array_equal(r["owner"][0], o["flag"])
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_qss_synthetic_tables(impl):
+    d = golden("sim_synthetic_tables")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    for tag in ("n8", "n64", "n257"):
+        sb = np.sin(d[tag + "_in_BANK"])
+        o = O.qss(d[tag + "_in_X"], d[tag + "_in_Y"], d[tag + "_in_CURVATURE"], sb, ov, 0)
+        r = H.qss(impl, d[tag + "_in_X"][None], d[tag + "_in_Y"][None], d[tag + "_in_CURVATURE"][None], sb, hv)
+        assert np.array_equal(r["v"][0], o["v"]) and np.array_equal(r["time"][0], o["time"])
+
+
+def test_generic_spline_eval_k5():
+    d = golden("sim_s30k5_i5")
+    x, y, yaw, rad = H.eval_spline(d["spl_t"], d["spl_cx"], d["spl_cy"], 5, d["ts"])
+    assert np.array_equal(x, d["in_X"]) and np.array_equal(y, d["in_Y"])
+    assert np.max(np.abs(rad - d["in_CURVATURE"]) / d["in_CURVATURE"]) < 1e-15
