@@ -144,6 +144,12 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
                      int M, int N, int B, int ld, const sto_vehicle_f64* vehicle, int impl, double* lap,
                      int32_t* status, void* work, size_t work_bytes, void* stream);
 
+/* Stage timing of sto_lap_time_f64 for roofline reports: after sto_set_stage_timing(1), each call records CUDA
+ * events on its stream around its four kernels (status reset, fit, sample, QSS); sto_last_stage_ms waits for the
+ * last call of this thread and returns their durations in milliseconds.  Off by default. */
+int sto_set_stage_timing(int on);
+int sto_last_stage_ms(float* ms4);
+
 /*
  * Same with HOST buffers (the call a ctypes binding makes): offsets_host[B][M] CANDIDATE-major as a user
  * holds them (row b = one line), track arrays [M], ts[N], lap_host[B], status_host[B].  Copies inputs to the

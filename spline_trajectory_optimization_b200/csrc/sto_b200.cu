@@ -195,6 +195,21 @@ __global__ void argmin_kernel(const double* lap, const int32_t* status, int B, d
     }
 }
 
+// Optional stage timing of the fused path (bench.py's roofline leg): CUDA events recorded on the launching
+// stream between the stages; nothing synchronises until sto_last_stage_ms() is called.
+struct StageTimer {
+    bool on = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool recorded = false;
+};
+thread_local StageTimer g_timer;
+inline void stage_mark(int i, cudaStream_t st) {
+    if (!g_timer.on) return;
+    if (!g_timer.ev[i]) cudaEventCreate(&g_timer.ev[i]);
+    cudaEventRecord(g_timer.ev[i], st);
+    if (i == 4) g_timer.recorded = true;
+}
+
 int check_vehicle(const sto_vehicle_f64* v) {
     if (!v) return fail(STO_ERR_INVALID, "vehicle is NULL");
     if (v->n_acc < 2 || v->n_acc > STO_MAX_BREAKS || v->n_dcc < 2 || v->n_dcc > STO_MAX_BREAKS)
@@ -378,23 +393,43 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     LapWork w = carve_lap(c, M, N, (size_t)ld, impl);
     if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "lap workspace too small");
     const int block = pick_block(B), grid = grid_for(B, block);
+    stage_mark(0, st);
     zero_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(status, B);
+    stage_mark(1, st);
     sto::FitArgs F{};
     F.cenx = centre_x; F.ceny = centre_y; F.nrmx = normal_x; F.nrmy = normal_y; F.off = offsets;
     F.M = M; F.B = B; F.ld = ld; F.u = w.u; F.cx = w.cx; F.cy = w.cy; F.status = status;
     F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz;
     fit_kernel<<<grid, block, 0, st>>>(F);
     STO_CUDA(cudaGetLastError());
+    stage_mark(2, st);
     // lap-only: x, y, yaw are never materialised; the chords and the radius are all the QSS reads
     sto::EvalArgs E{w.u, w.cx, w.cy, ts, M, N, B, ld, nullptr, nullptr, nullptr, w.R, w.qss.dd, w.qss.df};
     eval_kernel<<<grid, block, 0, st>>>(E);
     STO_CUDA(cudaGetLastError());
+    stage_mark(3, st);
     sto::QssArgs A{};
     A.dd = w.qss.dd; A.df = w.qss.df; A.R = w.R; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = ld; A.cap = w.qss.cap;
     A.v = w.qss.v; A.a = w.qss.a; A.rowflag = w.qss.rowflag;
     A.sp_ent = w.qss.sp_ent; A.sp_ext = w.qss.sp_ext; A.sp_turn = w.qss.sp_turn; A.sp_flag = w.qss.sp_flag;
     A.lap = lap; A.status = status;
-    return launch_qss(A, w.qss, vehicle, impl, false, st);
+    int rc = launch_qss(A, w.qss, vehicle, impl, false, st);
+    stage_mark(4, st);
+    return rc;
+}
+
+int sto_set_stage_timing(int on) {
+    g_timer.on = on != 0;
+    g_timer.recorded = false;
+    return STO_OK;
+}
+
+int sto_last_stage_ms(float* ms4) {
+    if (!ms4) return fail(STO_ERR_INVALID, "ms4 is NULL");
+    if (!g_timer.on || !g_timer.recorded) return fail(STO_ERR_INVALID, "no timed sto_lap_time_f64 call on this thread");
+    STO_CUDA(cudaEventSynchronize(g_timer.ev[4]));
+    for (int i = 0; i < 4; ++i) STO_CUDA(cudaEventElapsedTime(&ms4[i], g_timer.ev[i], g_timer.ev[i + 1]));
+    return STO_OK;
 }
 
 int sto_transpose_f64(const double* src, int rows, int cols, int ld_src, double* dst, int ld_dst, void* stream) {
