@@ -231,8 +231,18 @@ STO_HD void memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx
     }
 }
 
+#if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define STO_CLK(k) { long long c_ = clock64(); dbg_acc[k] += c_ - dbg_t; dbg_t = c_; }
+#else
+#define STO_CLK(k)
+#endif
+
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const sto_vehicle_f64& V, int b, bool active) {
     const int N = A.N, ld = A.ld;
+#if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long dbg_t = clock64();
+#endif
     const double lat0 = max_lat_acc(V, 0.0);
     MemoCtx C;
     C.liveB = Ring{W.liveB, ld, b, N, W.W}; C.liveF = Ring{W.liveF, ld, b, N, W.W};
@@ -259,13 +269,18 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const sto_ve
         const bool done = (nliveB == 0 && nliveF == 0 && nsp == 0) || status != 0;
         if (warp_all(done)) break;
         int nnew = 0;
+        STO_CLK(0)
         memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nsp, nnew, nliveB, steps, status);
+        STO_CLK(1)
         memo_spawned_rows<false>(A, W, C, V, b, done, lat0, nsp, nnew, steps, status);
+        STO_CLK(2)
         memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nsp, nnew, nliveF, steps, status);
+        STO_CLK(3)
         {
             int dummy = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
             memo_spawned_rows<true>(A, W, C, V, b, done, lat0, nsp, dummy, steps, status);
         }
+        STO_CLK(4)
         {   // append new rows, drop rows with both fronts stopped (simulator.py:351-356)
             const int tot = done ? 0 : nsp + nnew;
             const int nmax = warp_max(tot);
@@ -283,13 +298,19 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const sto_ve
             }
             if (!done) nsp = wr;
         }
+        STO_CLK(5)
         if (!done) {
             s = (s + 1 == N) ? 0 : s + 1;
             ++iters;
             if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
         }
     }
+    STO_CLK(6)
     if (active) qss_finish(A, b, status, steps, iters);
+    STO_CLK(7)
+#if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];
+#endif
 }
 
 }  // namespace sto

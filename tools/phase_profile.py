@@ -1,0 +1,45 @@
+"""Developer tool (GPU): per-phase SM-clock breakdown of qss_memo_kernel.  Builds a second copy of the library with
+-DSTO_PHASE_CLOCKS (clock64() deltas accumulated per thread, returned through the summary rows) and runs the
+BASELINE config-2 batch through the fit/sample/QSS stages.  Not part of the product."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from spline_trajectory_optimization_b200 import _lib, build  # noqa: E402
+
+alt = os.path.join(ROOT, "gpurun_out", "libsto_b200_phase.so")
+os.makedirs(os.path.dirname(alt), exist_ok=True)
+cmd = [build.nvcc_path()] + [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DSTO_PHASE_CLOCKS", "-o", alt,
+       os.path.join(build.CSRC, "sto_b200.cu")]
+subprocess.check_call(cmd)
+_lib.LIB_PATH = alt
+import bench  # noqa: E402
+from spline_trajectory_optimization_b200.evaluator import BatchedLineEvaluator, run_qss  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+rt, veh = bench.build_track(), bench.test_vehicle()
+ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), veh, impl="memo")
+off = ev.to_sample_major(torch.from_numpy(bench.make_offsets(rt, B, 1234)).cuda())
+u, cx, cy, st = ev.fit(off, B=B)
+S = ev.sample(u, cx, cy, B=B, want=("x", "y", "radius"))
+for _ in range(2):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = run_qss(S["x"], S["y"], S["radius"], ev.vehicle, B=B, impl=_lib.QSS_MEMO, profiles=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print("qss ms (incl. chord kernel)", e0.elapsed_time(e1))
+summ = res["summary"][:, :B].cpu().numpy()
+names = ["loop head", "orig backward", "spawned backward", "orig forward", "spawned forward", "compaction",
+         "loop tail", "finish"]
+tot = summ.sum(axis=0)
+print("per-thread total clocks: mean %.3g  (%.1f ms at 1.965 GHz)" % (tot.mean(), tot.mean() / 1.965e6))
+for k, n in enumerate(names):
+    print("%-18s %6.2f %%   mean clocks %.3g" % (n, 100 * summ[k].mean() / tot.mean(), summ[k].mean()))
