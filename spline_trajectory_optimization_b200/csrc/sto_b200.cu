@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -132,15 +133,28 @@ __global__ void chord_kernel(const double* x, const double* y, int N, int B, int
     df[sto::at(i, ld, b)] = sto::chord_norm(x0, y0, x1, y1);
 }
 
-template <bool OWNER>
-__global__ void qss_plain_kernel(sto::QssArgs A, const __grid_constant__ sto_vehicle_f64 V) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    sto::qss_plain_candidate<OWNER>(A, V, b < A.B ? b : A.B - 1, b < A.B);
+// The QSS kernels are latency bound (one dependent chain of FP64 divisions / square roots and scattered loads per
+// candidate), so what matters is how many warps each SM can interleave.  `lanes` candidates share a warp
+// (lanes = 32 for big batches); small batches are spread over more warps by leaving lanes idle.
+__device__ __forceinline__ int candidate_of_thread(int lanes, int B, bool& active) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
+    const int b = warp * lanes + lane;
+    active = lane < lanes && b < B;
+    return active ? b : B - 1;
 }
 
-__global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, const __grid_constant__ sto_vehicle_f64 V) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    sto::qss_memo_candidate(A, W, V, b < A.B ? b : A.B - 1, b < A.B);
+template <bool OWNER>
+__global__ void qss_plain_kernel(sto::QssArgs A, int lanes, const __grid_constant__ sto_vehicle_f64 V) {
+    bool active;
+    const int b = candidate_of_thread(lanes, A.B, active);
+    sto::qss_plain_candidate<OWNER>(A, V, b, active);
+}
+
+__global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int lanes, const __grid_constant__ sto_vehicle_f64 V) {
+    bool active;
+    const int b = candidate_of_thread(lanes, A.B, active);
+    sto::qss_memo_candidate(A, W, V, b, active);
 }
 
 __global__ void zero_status_kernel(int32_t* s, int B) {
@@ -217,16 +231,29 @@ int check_vehicle(const sto_vehicle_f64* v) {
     return STO_OK;
 }
 
+// Candidates per warp for the QSS kernels: aim for >= 8 warps on each of the 148 SMs before filling warps.
+int pick_lanes(int B) {
+    if (const char* e = getenv("STO_QSS_LANES")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
+    }
+    int lanes = 32;
+    while (lanes > 1 && (B + lanes - 1) / lanes < 148 * 8) lanes >>= 1;
+    return lanes;
+}
+
 int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* vehicle, int impl, bool owner,
                cudaStream_t st) {
-    const int block = pick_block(A.B);
-    const int grid = grid_for(A.B, block);
+    const int lanes = pick_lanes(A.B);
+    const int warps = (A.B + lanes - 1) / lanes;
+    const int block = 64;
+    const int grid = (warps * 32 + block - 1) / block;
     impl = effective_impl(A.N, impl);
     if (impl == STO_QSS_PLAIN) {
-        if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, *vehicle);
-        else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, *vehicle);
+        if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
+        else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
-        qss_memo_kernel<<<grid, block, 0, st>>>(A, w.memo, *vehicle);
+        qss_memo_kernel<<<grid, block, 0, st>>>(A, w.memo, lanes, *vehicle);
     }
     STO_CUDA(cudaGetLastError());
     return STO_OK;

@@ -28,8 +28,9 @@ struct MemoWork {
     unsigned long long *liveB, *liveF;  // [W][ld] rows whose backward / forward front is still running
     unsigned long long *contB, *stopB;  // [W][ld] memo of edge p -> p-1, indexed by p
     unsigned long long *contF, *stopF;  // [W][ld] memo of edge p -> p+1, indexed by p
-    int32_t *sp_ent, *sp_ext;           // [cap][ld] re-spawned rows (turn is not needed: owner untracked)
-    uint8_t* sp_flag;                   // [cap][ld]
+    int32_t *spB, *spF;                 // [cap][ld] live re-spawned fronts (backward / forward) as VIRTUAL ROW
+                                        // indices, creation order: a front at sample p with offset s = (k-1) mod N
+                                        // behaves like original row (p + s) mod N (backward) / (p - s) mod N (forward)
     int W;
 };
 
@@ -44,9 +45,8 @@ inline MemoWork carve_memo(Alloc alloc, int N, size_t ld, int cap) {
     w.stopB = (unsigned long long*)alloc(mb);
     w.contF = (unsigned long long*)alloc(mb);
     w.stopF = (unsigned long long*)alloc(mb);
-    w.sp_ent = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
-    w.sp_ext = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
-    w.sp_flag = (uint8_t*)alloc((size_t)cap * ld);
+    w.spB = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
+    w.spF = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
     return w;
 }
 
@@ -154,12 +154,14 @@ STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64&
     return true;
 }
 
-STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int nsp, int& nnew, int& status) {
-    if (nsp + nnew >= A.cap) { status |= STO_CAND_ROW_OVERFLOW; return; }
-    const int r = nsp + nnew;
-    W.sp_ent[at(r, A.ld, b)] = q;
-    W.sp_ext[at(r, A.ld, b)] = q;
-    W.sp_flag[at(r, A.ld, b)] = 0;
+// A new row at sample q (simulator.py:238-254).  It first acts in the next outer iteration (offset s+1), so its
+// virtual backward row is (q + s + 1) mod N; it is parked behind the live backward list ([nB, nB + nnew)) and
+// folded into both lists at the end of the iteration.
+STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s, int nB, int& nnew, int& status) {
+    if (nB + nnew >= A.cap) { status |= STO_CAND_ROW_OVERFLOW; return; }
+    int iv = q + s + 1;
+    if (iv >= A.N) iv -= A.N;
+    W.spB[at(nB + nnew, A.ld, b)] = iv;
     ++nnew;
 }
 
@@ -196,7 +198,7 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             if (stop.test(p)) stopped = true;
             else stopped = memo_step<FWD>(A, C, V, b, p, q, lat0, status, spawn, changed);
             if (stopped) { L &= ~bit; --nlive; }
-            if (spawn) memo_spawn(A, W, b, q, nsp, nnew, status);
+            if (spawn) memo_spawn(A, W, b, q, s, nsp, nnew, status);
             if (changed) att = L & ~cont.window(start) & ~donemask;  // later rows may now face a dirty edge
             else att &= ~donemask;
         }
@@ -204,31 +206,52 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
     }
 }
 
-// One sub-pass over the re-spawned rows (creation order).
+// One sub-pass over the live re-spawned fronts of one direction (creation order).  The list is compacted in
+// place while it is walked (fronts that stop are dropped); four entries and their memo words are fetched ahead so
+// the common case - every front on a known-clean edge - costs two overlapped memory round trips per four fronts.
 template <bool FWD>
-STO_HD void memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                              int b, bool done, double lat0, int nsp, int& nnew, int64_t& steps, int& status) {
+STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                             int b, bool done, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
+                             int& status) {
     const int N = A.N, ld = A.ld;
     const Ring& cont = FWD ? C.contF : C.contB;
     const Ring& stop = FWD ? C.stopF : C.stopB;
-    int32_t* pos = FWD ? W.sp_ext : W.sp_ent;
-    const uint8_t mybit = FWD ? 2 : 1;
-    const int nmax = warp_max(done ? 0 : nsp);
-    for (int r = 0; r < nmax; ++r) {
-        if (done || r >= nsp) continue;
-        const uint8_t f = W.sp_flag[at(r, ld, b)];
-        if (f & mybit) continue;
-        const int p = pos[at(r, ld, b)];
-        const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-        pos[at(r, ld, b)] = q;
-        ++steps;
-        if (cont.test(p)) continue;
-        bool stopped, changed = false, spawn = false;
-        if (stop.test(p)) stopped = true;
-        else stopped = memo_step<FWD>(A, C, V, b, p, q, lat0, status, spawn, changed);
-        if (stopped) W.sp_flag[at(r, ld, b)] = f | mybit;
-        if (spawn) memo_spawn(A, W, b, q, nsp, nnew, status);
+    int32_t* list = FWD ? W.spF : W.spB;
+    const int nmax = warp_max(done ? 0 : nlist);
+    int w = 0;
+    for (int r0 = 0; r0 < nmax; r0 += 4) {
+        if (done || r0 >= nlist) continue;
+        int iv[4], pp[4];
+        u64 cw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) iv[j] = (r0 + j < nlist) ? list[at(r0 + j, ld, b)] : -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int p = FWD ? iv[j] + s : iv[j] - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            pp[j] = p;
+            cw[j] = (iv[j] >= 0) ? cont.word(p >> 6) : 0ull;
+        }
+        bool touched = false;  // a memo may have changed since the prefetch
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (iv[j] < 0) continue;
+            const int p = pp[j];
+            ++steps;
+            const bool clean = touched ? cont.test(p) : (bool)((cw[j] >> (p & 63)) & 1ull);
+            bool stopped = false;
+            if (!clean) {
+                const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+                bool changed = false, spawn = false;
+                if (stop.test(p)) stopped = true;
+                else { stopped = memo_step<FWD>(A, C, V, b, p, q, lat0, status, spawn, changed); touched = true; }
+                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            }
+            if (!stopped) { list[at(w, ld, b)] = iv[j]; ++w; }
+        }
     }
+    return done ? nlist : w;
 }
 
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
@@ -263,40 +286,42 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const sto_ve
         }
     }
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
-    int nsp = 0, s = 0, iters = 0;
+    int nB = 0, nF = 0;  // live re-spawned fronts per direction
+    int s = 0, iters = 0;
     int64_t steps = 0;
     for (;;) {
-        const bool done = (nliveB == 0 && nliveF == 0 && nsp == 0) || status != 0;
+        const bool done = (nliveB == 0 && nliveF == 0 && nB == 0 && nF == 0) || status != 0;
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
-        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nsp, nnew, nliveB, steps, status);
+        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status);
         STO_CLK(1)
-        memo_spawned_rows<false>(A, W, C, V, b, done, lat0, nsp, nnew, steps, status);
+        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);
         STO_CLK(2)
-        memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nsp, nnew, nliveF, steps, status);
-        STO_CLK(3)
         {
-            int dummy = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
-            memo_spawned_rows<true>(A, W, C, V, b, done, lat0, nsp, dummy, steps, status);
+            int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
+            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status);
+        }
+        STO_CLK(3)
+        int wF;
+        {
+            int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
+            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status);
         }
         STO_CLK(4)
-        {   // append new rows, drop rows with both fronts stopped (simulator.py:351-356)
-            const int tot = done ? 0 : nsp + nnew;
-            const int nmax = warp_max(tot);
-            int wr = 0;
-            for (int r = 0; r < nmax; ++r) {
-                if (r >= tot) continue;
-                const uint8_t f = W.sp_flag[at(r, ld, b)];
-                if (f == 3) continue;
-                if (wr != r) {
-                    W.sp_ent[at(wr, ld, b)] = W.sp_ent[at(r, ld, b)];
-                    W.sp_ext[at(wr, ld, b)] = W.sp_ext[at(r, ld, b)];
-                    W.sp_flag[at(wr, ld, b)] = f;
-                }
-                ++wr;
+        if (!done) {
+            // fold the rows spawned in this iteration behind both lists (simulator.py:351-356)
+            if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
+            for (int j = 0; j < nnew; ++j) {
+                const int ivb = W.spB[at(nB + j, ld, b)];   // (q + s + 1) mod N
+                int ivf = ivb - 2 * (s + 1);                 // (q - (s + 1)) mod N
+                ivf %= N;
+                if (ivf < 0) ivf += N;
+                W.spB[at(wB + j, ld, b)] = ivb;
+                W.spF[at(wF + j, ld, b)] = ivf;
             }
-            if (!done) nsp = wr;
+            nB = wB + nnew;
+            nF = wF + nnew;
         }
         STO_CLK(5)
         if (!done) {
