@@ -77,8 +77,11 @@ struct QssWork {
     sto::MemoWork memo;
     int cap;
 };
+constexpr size_t kMemoSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use on sm_100a
 inline int effective_impl(int N, int impl) {
-    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N) ? STO_QSS_MEMO : STO_QSS_PLAIN;
+    // the memoised kernel keeps six bit planes per candidate in shared memory: 48 * ceil(N/64) bytes
+    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N && sto::memo_plane_bytes(N) <= kMemoSmemBudget)
+               ? STO_QSS_MEMO : STO_QSS_PLAIN;
 }
 QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool need_state) {
     QssWork w{};
@@ -151,10 +154,15 @@ __global__ void qss_plain_kernel(sto::QssArgs A, int lanes, const __grid_constan
     sto::qss_plain_candidate<OWNER>(A, V, b, active);
 }
 
+extern __shared__ unsigned long long sto_planes[];  // [6 planes][W words][lanes] per warp, one column per lane
+
 __global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int lanes, const __grid_constant__ sto_vehicle_f64 V) {
     bool active;
     const int b = candidate_of_thread(lanes, A.B, active);
-    sto::qss_memo_candidate(A, W, V, b, active);
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    unsigned long long* base = sto_planes + (size_t)warp_in_block * 6 * W.W * lanes;
+    const sto::MemoCtx C = sto::memo_bind(base, lanes, lane < lanes ? lane : 0, A.N, W.W);
+    sto::qss_memo_candidate(A, W, C, V, b, active);
 }
 
 __global__ void zero_status_kernel(int32_t* s, int B) {
@@ -231,29 +239,36 @@ int check_vehicle(const sto_vehicle_f64* v) {
     return STO_OK;
 }
 
-// Candidates per warp for the QSS kernels: aim for >= 8 warps on each of the 148 SMs before filling warps.
-int pick_lanes(int B) {
+// Candidates per warp for the QSS kernels: aim for a few warps on each of the 148 SMs before filling warps.
+int pick_lanes(int B, size_t smem_per_candidate) {
+    int lanes = 32;
     if (const char* e = getenv("STO_QSS_LANES")) {
         int v = atoi(e);
-        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
+    } else {
+        while (lanes > 4 && (B + lanes - 1) / lanes < 148 * 2) lanes >>= 1;
     }
-    int lanes = 32;
-    while (lanes > 1 && (B + lanes - 1) / lanes < 148 * 8) lanes >>= 1;
+    while (lanes > 1 && smem_per_candidate * lanes > kMemoSmemBudget) lanes >>= 1;
     return lanes;
 }
 
 int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* vehicle, int impl, bool owner,
                cudaStream_t st) {
-    const int lanes = pick_lanes(A.B);
-    const int warps = (A.B + lanes - 1) / lanes;
-    const int block = 64;
-    const int grid = (warps * 32 + block - 1) / block;
     impl = effective_impl(A.N, impl);
     if (impl == STO_QSS_PLAIN) {
+        const int lanes = pick_lanes(A.B, 0);
+        const int warps = (A.B + lanes - 1) / lanes;
+        const int block = 64;
+        const int grid = (warps * 32 + block - 1) / block;
         if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
         else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
-        qss_memo_kernel<<<grid, block, 0, st>>>(A, w.memo, lanes, *vehicle);
+        const size_t per_cand = sto::memo_plane_bytes(A.N);
+        const int lanes = pick_lanes(A.B, per_cand);
+        const int warps = (A.B + lanes - 1) / lanes;
+        const size_t smem = per_cand * lanes;  // one warp per CTA
+        STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qss_memo_kernel<<<warps, 32, smem, st>>>(A, w.memo, lanes, *vehicle);
     }
     STO_CUDA(cudaGetLastError());
     return STO_OK;

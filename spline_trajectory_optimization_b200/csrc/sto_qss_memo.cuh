@@ -25,32 +25,31 @@
 namespace sto {
 
 struct MemoWork {
-    unsigned long long *liveB, *liveF;  // [W][ld] rows whose backward / forward front is still running
-    unsigned long long *contB, *stopB;  // [W][ld] memo of edge p -> p-1, indexed by p
-    unsigned long long *contF, *stopF;  // [W][ld] memo of edge p -> p+1, indexed by p
-    int32_t *spB, *spF;                 // [cap][ld] live re-spawned fronts (backward / forward) as VIRTUAL ROW
-                                        // indices, creation order: a front at sample p with offset s = (k-1) mod N
-                                        // behaves like original row (p + s) mod N (backward) / (p - s) mod N (forward)
-    int W;
+    int32_t *spB, *spF;  // [cap][ld] (global) live re-spawned fronts (backward / forward) as VIRTUAL ROW indices in
+                         // creation order: a front at sample p with offset s = (k-1) mod N behaves like original
+                         // row (p + s) mod N (backward) / (p - s) mod N (forward)
+    int W;               // 64-bit words per bit plane = ceil(N / 64)
 };
+
+// Bytes of bit-plane storage per candidate (six planes: live B/F, cont B/F, stop B/F).  On the device the planes
+// live in SHARED memory (private column per lane): every memo test / update is a ~30-cycle LDS/STS instead of a
+// dependent global round trip - the v1 profile spent >70 % of its time on those (profiles/r01_*).
+STO_HD size_t memo_plane_bytes(int N) { return (size_t)6 * (size_t)((N + 63) / 64) * sizeof(unsigned long long); }
 
 template <class Alloc>
 inline MemoWork carve_memo(Alloc alloc, int N, size_t ld, int cap) {
     MemoWork w;
     w.W = (N + 63) / 64;
-    const size_t mb = (size_t)w.W * ld * sizeof(unsigned long long);
-    w.liveB = (unsigned long long*)alloc(mb);
-    w.liveF = (unsigned long long*)alloc(mb);
-    w.contB = (unsigned long long*)alloc(mb);
-    w.stopB = (unsigned long long*)alloc(mb);
-    w.contF = (unsigned long long*)alloc(mb);
-    w.stopF = (unsigned long long*)alloc(mb);
     w.spB = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
     w.spF = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
     return w;
 }
 
 typedef unsigned long long u64;
+#if defined(STO_HOSTSIM_COUNTERS)
+static long long g_memo_evals[2] = {0, 0};   // host-side test instrumentation only
+static long long g_memo_words[2] = {0, 0};
+#endif
 
 STO_HD int ctz64(u64 x) {
 #if defined(__CUDA_ARCH__)
@@ -74,15 +73,15 @@ STO_HD bool same_bits(double a, double b) {
 #endif
 }
 
-// One candidate's view of a [W][ld] bit set over a ring of N positions (bits >= N of the last word stay 0).
+// One candidate's bit set over a ring of N positions: word w at m[w * stride] (bits >= N of the last word stay 0).
 struct Ring {
     u64* m;
-    int ld, b, N, W;
-    STO_HD u64 word(int w) const { return m[at(w, ld, b)]; }
-    STO_HD void set_word(int w, u64 x) const { m[at(w, ld, b)] = x; }
+    int stride, N, W;
+    STO_HD u64 word(int w) const { return m[(size_t)w * stride]; }
+    STO_HD void set_word(int w, u64 x) const { m[(size_t)w * stride] = x; }
     STO_HD bool test(int p) const { return (word(p >> 6) >> (p & 63)) & 1ull; }
-    STO_HD void set(int p) const { m[at(p >> 6, ld, b)] |= (1ull << (p & 63)); }
-    STO_HD void clear(int p) const { m[at(p >> 6, ld, b)] &= ~(1ull << (p & 63)); }
+    STO_HD void set(int p) const { m[(size_t)(p >> 6) * stride] |= (1ull << (p & 63)); }
+    STO_HD void clear(int p) const { m[(size_t)(p >> 6) * stride] &= ~(1ull << (p & 63)); }
     // 64 bits starting at bit `pos` (no ring wrap; bits past the last word read as 0)
     STO_HD u64 read64(int pos) const {
         const int w = pos >> 6, sh = pos & 63;
@@ -100,51 +99,86 @@ struct Ring {
     }
 };
 
+// The six planes of one candidate: plane k, word w at base[(k * W + w) * stride] (base already offset by the lane).
+// Rings are formed on the fly from (kind, direction) so that nothing is indexed dynamically out of registers.
 struct MemoCtx {
-    Ring liveB, liveF, contB, stopB, contF, stopF;
+    u64* base;
+    int stride, N, W;
+    STO_HD Ring plane(int k) const { return Ring{base + (size_t)k * W * stride, stride, N, W}; }
+    STO_HD Ring live(int d) const { return plane(0 + d); }   // d = 0 backward (edge p -> p-1), 1 forward (p -> p+1)
+    STO_HD Ring cont(int d) const { return plane(2 + d); }
+    STO_HD Ring stop(int d) const { return plane(4 + d); }
 };
+
+STO_HD MemoCtx memo_bind(u64* base, int stride, int lane, int N, int W) {
+    return MemoCtx{base + lane, stride, N, W};
+}
 
 // The stored state of sample j changed: forget every memo that read it.
 STO_HD void memo_invalidate(const MemoCtx& C, int j, int N) {
     const int jn = (j + 1 == N) ? 0 : j + 1, jp = (j == 0) ? N - 1 : j - 1;
-    C.contB.clear(j);  C.stopB.clear(j);    // edge j -> j-1
-    C.contB.clear(jn); C.stopB.clear(jn);   // edge j+1 -> j
-    C.contF.clear(j);  C.stopF.clear(j);    // edge j -> j+1
-    C.contF.clear(jp); C.stopF.clear(jp);   // edge j-1 -> j
+    C.cont(0).clear(j);  C.stop(0).clear(j);    // edge j -> j-1
+    C.cont(0).clear(jn); C.stop(0).clear(jn);   // edge j+1 -> j
+    C.cont(1).clear(j);  C.stop(1).clear(j);    // edge j -> j+1
+    C.cont(1).clear(jp); C.stop(1).clear(jp);   // edge j-1 -> j
+}
+
+// front_step<FWD> of sto_qss.cuh with the direction as a run-time value (lanes of one warp may be in different
+// sub-passes): the same operations on the same operands, selected instead of branched, so results are bit-identical.
+STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double dd, double Rq,
+                          double gsbq, double& g, double& vp2) {
+    double dt = dd / vp;
+    double md = dt * V.max_jerk;
+    double hi = ap + md, lo = ap - md;
+    double vacc = ppoly4(V.acc_x, V.acc_c, V.n_acc, vp);
+    double vdcc = ppoly4(V.dcc_x, V.dcc_c, V.n_dcc, vp);
+    hi = np_clip(hi, vdcc, vacc);
+    lo = np_clip(lo, vdcc, vacc);
+    vp2 = vp * vp;
+    const double th = 2 * hi * dd, tl = 2 * lo * dd;
+    const double s_hi = sqrt(py_max(fwd ? th + vp2 : vp2 - th, 0.0));
+    const double s_lo = sqrt(py_max(fwd ? tl + vp2 : vp2 - tl, 0.0));
+    const double smax = fwd ? s_hi : s_lo, smin = fwd ? s_lo : s_hi;
+    double mc = calc_v(max_lat_acc(V, ap), Rq, gsbq);
+    g = py_min3(smax, mc, V.max_speed);
+    return smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
 }
 
 // Evaluate the front step p -> q, apply it and record its memo.  Returns true when the front stops.
-template <bool FWD>
-STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64& V, int b, int p, int q,
+STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64& V, int b, bool fwd, int p, int q,
                       double lat0, int& status, bool& spawn, bool& changed) {
     const int ld = A.ld, N = A.N;
+    const int d = fwd ? 1 : 0;
+    // all six state words are fetched up front: one overlapped memory round trip per evaluation
     const double vp = A.v[at(p, ld, b)], ap = A.a[at(p, ld, b)];
-    const double dd = A.dd[at(FWD ? p : q, ld, b)];
+    const double dd = A.dd[at(fwd ? p : q, ld, b)];
     const double Rq = A.R[at(q, ld, b)], gq = gsb_at(A, q);
+    const double vq = A.v[at(q, ld, b)], aq_old = A.a[at(q, ld, b)];
     spawn = false;
     changed = false;
+#if defined(STO_HOSTSIM_COUNTERS)
+    ++g_memo_evals[d];
+#endif
     if (vp == 0.0) { status |= STO_CAND_ZERO_SPEED; return true; }
-    const Ring& cont = FWD ? C.contF : C.contB;
-    const Ring& stop = FWD ? C.stopF : C.stopB;
     double g, vp2;
-    const bool valid = front_step<FWD>(V, vp, ap, dd, Rq, gq, g, vp2);
+    const bool valid = front_step_rt(V, fwd, vp, ap, dd, Rq, gq, g, vp2);
     if (valid) {
-        const double vq = A.v[at(q, ld, b)];
-        if (vq < g) { stop.set(p); cont.clear(p); return true; }
-        const double aq = FWD ? (g * g - vp2) / (2 * dd) : (vp2 - g * g) / (2 * dd);
-        if (!same_bits(vq, g) || !same_bits(A.a[at(q, ld, b)], aq)) {
+        if (vq < g) { C.stop(d).set(p); C.cont(d).clear(p); return true; }
+        const double gg = g * g;
+        const double aq = (fwd ? gg - vp2 : vp2 - gg) / (2 * dd);
+        if (!same_bits(vq, g) || !same_bits(aq_old, aq)) {
             A.v[at(q, ld, b)] = g;
             A.a[at(q, ld, b)] = aq;
             memo_invalidate(C, q, N);
             changed = true;
         }
-        cont.set(p);  // re-running this step on the state as it now stands rewrites the same values
-        stop.clear(p);
+        C.cont(d).set(p);  // re-running this step on the state as it now stands rewrites the same values
+        C.stop(d).clear(p);
         return false;
     }
-    if (FWD) { stop.set(p); cont.clear(p); return true; }
+    if (fwd) { C.stop(1).set(p); C.cont(1).clear(p); return true; }
     const double vi = init_speed(lat0, Rq, gq, V.max_speed);
-    if (!same_bits(A.v[at(q, ld, b)], vi) || !same_bits(A.a[at(q, ld, b)], 0.0)) {
+    if (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) {
         A.v[at(q, ld, b)] = vi;
         A.a[at(q, ld, b)] = 0.0;
         memo_invalidate(C, q, N);
@@ -165,174 +199,149 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
     ++nnew;
 }
 
-// One sub-pass over the original rows.  s = (k-1) mod N.
-template <bool FWD>
-STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                               int b, bool done, int s, double lat0, int nsp, int& nnew, int& nlive,
-                               int64_t& steps, int& status) {
-    const int N = A.N;
-    const Ring& live = FWD ? C.liveF : C.liveB;
-    const Ring& cont = FWD ? C.contF : C.contB;
-    const Ring& stop = FWD ? C.stopF : C.stopB;
-    for (int w = 0; w < W.W; ++w) {
-        if (done) continue;
-        u64 L = live.word(w);
-        if (!L) continue;
-        steps += popc64(L);
-        // row i = 64 w + t sits at sample (i -/+ s) mod N
-        int start = FWD ? (64 * w + s) : (64 * w - s);
-        if (start >= N) start -= N;
-        if (start < 0) start += N;
-        u64 att = L & ~cont.window(start);  // fronts that are not on a known-clean edge
-        u64 donemask = 0;
-        while (att) {
-            const int t = ctz64(att);
-            const u64 bit = 1ull << t;
-            donemask |= bit | (bit - 1ull);
-            const int i = 64 * w + t;
-            int p = FWD ? i + s : i - s;
-            if (p >= N) p -= N;
-            if (p < 0) p += N;
-            const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-            bool stopped, changed = false, spawn = false;
-            if (stop.test(p)) stopped = true;
-            else stopped = memo_step<FWD>(A, C, V, b, p, q, lat0, status, spawn, changed);
-            if (stopped) { L &= ~bit; --nlive; }
-            if (spawn) memo_spawn(A, W, b, q, s, nsp, nnew, status);
-            if (changed) att = L & ~cont.window(start) & ~donemask;  // later rows may now face a dirty edge
-            else att &= ~donemask;
-        }
-        live.set_word(w, L);
-    }
-}
-
-// One sub-pass over the live re-spawned fronts of one direction (creation order).  The list is compacted in
-// place while it is walked (fronts that stop are dropped); four entries and their memo words are fetched ahead so
-// the common case - every front on a known-clean edge - costs two overlapped memory round trips per four fronts.
-template <bool FWD>
-STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                             int b, bool done, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
-                             int& status) {
-    const int N = A.N, ld = A.ld;
-    const Ring& cont = FWD ? C.contF : C.contB;
-    const Ring& stop = FWD ? C.stopF : C.stopB;
-    int32_t* list = FWD ? W.spF : W.spB;
-    const int nmax = warp_max(done ? 0 : nlist);
-    int w = 0;
-    for (int r0 = 0; r0 < nmax; r0 += 4) {
-        if (done || r0 >= nlist) continue;
-        int iv[4], pp[4];
-        u64 cw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) iv[j] = (r0 + j < nlist) ? list[at(r0 + j, ld, b)] : -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int p = FWD ? iv[j] + s : iv[j] - s;
-            if (p >= N) p -= N;
-            if (p < 0) p += N;
-            pp[j] = p;
-            cw[j] = (iv[j] >= 0) ? cont.word(p >> 6) : 0ull;
-        }
-        bool touched = false;  // a memo may have changed since the prefetch
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (iv[j] < 0) continue;
-            const int p = pp[j];
-            ++steps;
-            const bool clean = touched ? cont.test(p) : (bool)((cw[j] >> (p & 63)) & 1ull);
-            bool stopped = false;
-            if (!clean) {
-                const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-                bool changed = false, spawn = false;
-                if (stop.test(p)) stopped = true;
-                else { stopped = memo_step<FWD>(A, C, V, b, p, q, lat0, status, spawn, changed); touched = true; }
-                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
-            }
-            if (!stopped) { list[at(w, ld, b)] = iv[j]; ++w; }
-        }
-    }
-    return done ? nlist : w;
-}
-
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
 #define STO_CLK(k) { long long c_ = clock64(); dbg_acc[k] += c_ - dbg_t; dbg_t = c_; }
 #else
 #define STO_CLK(k)
 #endif
 
-STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const sto_vehicle_f64& V, int b, bool active) {
-    const int N = A.N, ld = A.ld;
+// The schedule as a per-lane state machine.  Each lane (candidate) walks its own sub-passes - original rows of the
+// backward sub-pass (64-row words against the ring-shifted memo window), live re-spawned backward fronts (list,
+// compacted in place), the same two for the forward sub-pass, then the end-of-iteration fold - until it reaches a
+// front that needs an FP64 evaluation.  The warp then evaluates one step for every lane at once: the expensive
+// code (divisions, square roots, scattered state loads) always runs convergent, and a warp needs about
+// max_lane(#evaluations) rounds instead of the sum over (sub-pass, word) of the per-lane maxima that a lock-step
+// walk costs (measured 2.3x more).  The search between evaluations touches only shared memory and the lists.
+STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
+                               bool active) {
+    const int N = A.N, ld = A.ld, NW = W.W;
+    const double lat0 = max_lat_acc(V, 0.0);
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long dbg_t = clock64();
 #endif
-    const double lat0 = max_lat_acc(V, 0.0);
-    MemoCtx C;
-    C.liveB = Ring{W.liveB, ld, b, N, W.W}; C.liveF = Ring{W.liveF, ld, b, N, W.W};
-    C.contB = Ring{W.contB, ld, b, N, W.W}; C.stopB = Ring{W.stopB, ld, b, N, W.W};
-    C.contF = Ring{W.contF, ld, b, N, W.W}; C.stopF = Ring{W.stopF, ld, b, N, W.W};
     int status = 0;
     if (active) {
         for (int i = 0; i < N; ++i) {  // simulator.py:133-147
             A.v[at(i, ld, b)] = init_speed(lat0, A.R[at(i, ld, b)], gsb_at(A, i), V.max_speed);
             A.a[at(i, ld, b)] = 0.0;
         }
-        for (int w = 0; w < W.W; ++w) {
+        for (int w = 0; w < NW; ++w) {
             const int nb = N - 64 * w;
             const u64 ones = (nb >= 64) ? ~0ull : ((1ull << nb) - 1ull);
-            C.liveB.set_word(w, ones); C.liveF.set_word(w, ones);
-            C.contB.set_word(w, 0); C.stopB.set_word(w, 0);
-            C.contF.set_word(w, 0); C.stopF.set_word(w, 0);
-        }
-    }
-    int nliveB = active ? N : 0, nliveF = active ? N : 0;
-    int nB = 0, nF = 0;  // live re-spawned fronts per direction
-    int s = 0, iters = 0;
-    int64_t steps = 0;
-    for (;;) {
-        const bool done = (nliveB == 0 && nliveF == 0 && nB == 0 && nF == 0) || status != 0;
-        if (warp_all(done)) break;
-        int nnew = 0;
-        STO_CLK(0)
-        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status);
-        STO_CLK(1)
-        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);
-        STO_CLK(2)
-        {
-            int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
-            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status);
-        }
-        STO_CLK(3)
-        int wF;
-        {
-            int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
-            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status);
-        }
-        STO_CLK(4)
-        if (!done) {
-            // fold the rows spawned in this iteration behind both lists (simulator.py:351-356)
-            if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
-            for (int j = 0; j < nnew; ++j) {
-                const int ivb = W.spB[at(nB + j, ld, b)];   // (q + s + 1) mod N
-                int ivf = ivb - 2 * (s + 1);                 // (q - (s + 1)) mod N
-                ivf %= N;
-                if (ivf < 0) ivf += N;
-                W.spB[at(wB + j, ld, b)] = ivb;
-                W.spF[at(wF + j, ld, b)] = ivf;
+            for (int d = 0; d < 2; ++d) {
+                C.live(d).set_word(w, ones);
+                C.cont(d).set_word(w, 0);
+                C.stop(d).set_word(w, 0);
             }
-            nB = wB + nnew;
-            nF = wF + nnew;
-        }
-        STO_CLK(5)
-        if (!done) {
-            s = (s + 1 == N) ? 0 : s + 1;
-            ++iters;
-            if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
         }
     }
-    STO_CLK(6)
+    STO_CLK(0)
+    enum { PH_OB = 0, PH_SB = 1, PH_OF = 2, PH_SF = 3, PH_FOLD = 4 };
+    int phase = PH_OB;
+    int nliveB = active ? N : 0, nliveF = active ? N : 0;  // original rows with a running backward / forward front
+    int nlistB = 0, nlistF = 0;                             // live re-spawned fronts per direction
+    int wlistB = 0, wlistF = 0;                             // compacted lengths after this iteration's passes
+    int nnew = 0, s = 0, iters = 0;
+    int64_t steps = 0;
+    // cursor over original rows: word w, its live bits L, the bits still needing attention, the bits already passed
+    int w = 0, start = 0;
+    u64 L = 0, att = 0, donemask = 0, cur_bit = 0;
+    bool word_open = false;
+    // cursor over a re-spawned list: read index r, write index wr
+    int r = 0, wr = 0, cur_iv = 0;
+    bool finished = !active;
+    for (;;) {
+        bool pending = false, fwd = false;
+        int p = 0, q = 0;
+        while (!finished && !pending) {
+            if (phase == PH_OB || phase == PH_OF) {
+                const int d = (phase == PH_OF) ? 1 : 0;
+                if (!word_open) {
+                    if ((d ? nliveF : nliveB) == 0 || w >= NW) { ++phase; r = 0; wr = 0; w = 0; continue; }
+                    L = C.live(d).word(w);
+                    if (!L) { ++w; continue; }
+#if defined(STO_HOSTSIM_COUNTERS)
+                    ++g_memo_words[d];
+#endif
+                    steps += popc64(L);
+                    start = d ? (64 * w + s) : (64 * w - s);  // row i = 64 w + t sits at sample (i -/+ s) mod N
+                    if (start >= N) start -= N;
+                    if (start < 0) start += N;
+                    att = L & ~C.cont(d).window(start);       // fronts that are not on a known-clean edge
+                    donemask = 0;
+                    word_open = true;
+                }
+                if (!att) { C.live(d).set_word(w, L); ++w; word_open = false; continue; }
+                const int t = ctz64(att);
+                cur_bit = 1ull << t;
+                donemask |= cur_bit | (cur_bit - 1ull);
+                const int i = 64 * w + t;
+                p = d ? i + s : i - s;
+                if (p >= N) p -= N;
+                if (p < 0) p += N;
+                if (C.stop(d).test(p)) { L &= ~cur_bit; if (d) --nliveF; else --nliveB; att &= ~donemask; continue; }
+                q = d ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+                fwd = d != 0;
+                pending = true;
+            } else if (phase == PH_SB || phase == PH_SF) {
+                const int d = (phase == PH_SF) ? 1 : 0;
+                int32_t* list = d ? W.spF : W.spB;
+                if (r >= (d ? nlistF : nlistB)) { if (d) wlistF = wr; else wlistB = wr; ++phase; w = 0; word_open = false; continue; }
+                cur_iv = list[at(r, ld, b)];
+                ++r;
+                ++steps;
+                p = d ? cur_iv + s : cur_iv - s;
+                if (p >= N) p -= N;
+                if (p < 0) p += N;
+                if (C.cont(d).test(p)) { list[at(wr, ld, b)] = cur_iv; ++wr; continue; }
+                if (C.stop(d).test(p)) continue;  // the front stops here: dropped from the list
+                q = d ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+                fwd = d != 0;
+                pending = true;
+            } else {  // PH_FOLD: append the rows spawned in this iteration behind both lists (simulator.py:351-356)
+                if (wlistF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
+                for (int j = 0; j < nnew; ++j) {
+                    const int ivb = W.spB[at(nlistB + j, ld, b)];     // (q + s + 1) mod N
+                    int ivf = (ivb - 2 * (s + 1)) % N;                 // (q - (s + 1)) mod N
+                    if (ivf < 0) ivf += N;
+                    W.spB[at(wlistB + j, ld, b)] = ivb;
+                    W.spF[at(wlistF + j, ld, b)] = ivf;
+                }
+                nlistB = wlistB + nnew;
+                nlistF = wlistF + nnew;
+                nnew = 0;
+                s = (s + 1 == N) ? 0 : s + 1;
+                ++iters;
+                if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
+                finished = (nliveB == 0 && nliveF == 0 && nlistB == 0 && nlistF == 0) || status != 0;
+                phase = PH_OB;
+                w = 0;
+                word_open = false;
+            }
+        }
+        STO_CLK(1)
+        if (warp_all(finished)) break;
+        if (pending) {
+            bool spawn, changed;
+            const bool stopped = memo_step(A, C, V, b, fwd, p, q, lat0, status, spawn, changed);
+            const int d = fwd ? 1 : 0;
+            if (spawn) memo_spawn(A, W, b, q, s, nlistB, nnew, status);
+            if (phase == PH_OB || phase == PH_OF) {
+                if (stopped) { L &= ~cur_bit; if (d) --nliveF; else --nliveB; }
+                // later rows of this word may now face a dirty edge: re-read the window after a state change
+                att = changed ? (L & ~C.cont(d).window(start) & ~donemask) : (att & ~donemask);
+            } else if (!stopped) {
+                int32_t* list = d ? W.spF : W.spB;
+                list[at(wr, ld, b)] = cur_iv;
+                ++wr;
+            }
+            if (status != 0) finished = true;
+        }
+        STO_CLK(2)
+    }
     if (active) qss_finish(A, b, status, steps, iters);
-    STO_CLK(7)
+    STO_CLK(3)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];
 #endif

@@ -2,6 +2,7 @@
 // spline_trajectory_optimization_b200/csrc/*.cuh for the host (g++, -ffp-contract=off) so the schedule logic
 // (row tables, ring windows, memoisation) can be unit-tested in the GPU-less authoring container.  Each
 // candidate runs as a "warp of one".  The product never builds, loads or falls back to this file.
+#define STO_HOSTSIM_COUNTERS 1
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -74,9 +75,17 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
         std::vector<std::vector<char>> keep;
         sto::MemoWork W = sto::carve_memo([&](size_t n) { keep.emplace_back(n); return (void*)keep.back().data(); },
                                           N, (size_t)ld, cap);
-        for (int b = 0; b < B; ++b) sto::qss_memo_candidate(A, W, *V, b, true);
+        std::vector<unsigned long long> planes((size_t)6 * W.W);   // a "warp of one": stride 1, lane 0
+        const sto::MemoCtx C = sto::memo_bind(planes.data(), 1, 0, N, W.W);
+        for (int b = 0; b < B; ++b) sto::qss_memo_candidate(A, W, C, *V, b, true);
     }
     return 0;
+}
+
+void hostsim_counters(long long* out4, int reset) {
+    out4[0] = sto::g_memo_evals[0]; out4[1] = sto::g_memo_evals[1];
+    out4[2] = sto::g_memo_words[0]; out4[3] = sto::g_memo_words[1];
+    if (reset) { sto::g_memo_evals[0] = sto::g_memo_evals[1] = sto::g_memo_words[0] = sto::g_memo_words[1] = 0; }
 }
 
 }  // extern "C"
