@@ -205,16 +205,91 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
 #define STO_CLK(k)
 #endif
 
-// The schedule as a per-lane state machine.  Each lane (candidate) walks its own sub-passes - original rows of the
-// backward sub-pass (64-row words against the ring-shifted memo window), live re-spawned backward fronts (list,
-// compacted in place), the same two for the forward sub-pass, then the end-of-iteration fold - until it reaches a
-// front that needs an FP64 evaluation.  The warp then evaluates one step for every lane at once: the expensive
-// code (divisions, square roots, scattered state loads) always runs convergent, and a warp needs about
-// max_lane(#evaluations) rounds instead of the sum over (sub-pass, word) of the per-lane maxima that a lock-step
-// walk costs (measured 2.3x more).  The search between evaluations touches only shared memory and the lists.
+// One sub-pass over the original rows, all lanes of the warp walking the same 64-row word together (the plane
+// words of the 32 candidates sit side by side in shared memory).  s = (k-1) mod N.
+template <bool FWD>
+STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                               int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive,
+                               int64_t& steps, int& status) {
+    const int N = A.N, d = FWD ? 1 : 0;
+    const Ring live = C.live(d), cont = C.cont(d), stop = C.stop(d);
+    for (int w = 0; w < W.W; ++w) {
+        if (skip) continue;
+        u64 L = live.word(w);
+        if (!L) continue;
+#if defined(STO_HOSTSIM_COUNTERS)
+        ++g_memo_words[d];
+#endif
+        steps += popc64(L);
+        // row i = 64 w + t sits at sample (i -/+ s) mod N
+        int start = FWD ? (64 * w + s) : (64 * w - s);
+        if (start >= N) start -= N;
+        if (start < 0) start += N;
+        u64 att = L & ~cont.window(start);  // fronts that are not on a known-clean edge
+        u64 donemask = 0;
+        while (att) {
+            const int t = ctz64(att);
+            const u64 bit = 1ull << t;
+            donemask |= bit | (bit - 1ull);
+            const int i = 64 * w + t;
+            int p = FWD ? i + s : i - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+            bool stopped, changed = false, spawn = false;
+            if (stop.test(p)) stopped = true;
+            else stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+            if (stopped) { L &= ~bit; --nlive; }
+            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            // later rows of this word may now face a dirty edge: re-read the window after a state change
+            att = changed ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
+        }
+        live.set_word(w, L);
+    }
+}
+
+// One sub-pass over the live re-spawned fronts of one direction (creation order).  The list is compacted in
+// place while it is walked (fronts that stop are dropped); four entries are fetched ahead so the common case -
+// every front on a known-clean edge - costs one overlapped global round trip per four fronts.
+template <bool FWD>
+STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                             int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
+                             int& status) {
+    const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
+    const Ring cont = C.cont(d), stop = C.stop(d);
+    int32_t* list = FWD ? W.spF : W.spB;
+    const int nmax = warp_max(skip ? 0 : nlist);
+    int w = 0;
+    for (int r0 = 0; r0 < nmax; r0 += 4) {
+        if (skip || r0 >= nlist) continue;
+        int iv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) iv[j] = (r0 + j < nlist) ? list[at(r0 + j, ld, b)] : -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (iv[j] < 0) continue;
+            int p = FWD ? iv[j] + s : iv[j] - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            ++steps;
+            bool stopped = false;
+            if (!cont.test(p)) {
+                const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+                bool changed = false, spawn = false;
+                if (stop.test(p)) stopped = true;
+                else stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            }
+            if (!stopped) { list[at(w, ld, b)] = iv[j]; ++w; }
+        }
+    }
+    return skip ? nlist : w;
+}
+
+// The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
                                bool active) {
-    const int N = A.N, ld = A.ld, NW = W.W;
+    const int N = A.N, ld = A.ld;
     const double lat0 = max_lat_acc(V, 0.0);
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -226,7 +301,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             A.v[at(i, ld, b)] = init_speed(lat0, A.R[at(i, ld, b)], gsb_at(A, i), V.max_speed);
             A.a[at(i, ld, b)] = 0.0;
         }
-        for (int w = 0; w < NW; ++w) {
+        for (int w = 0; w < W.W; ++w) {
             const int nb = N - 64 * w;
             const u64 ones = (nb >= 64) ? ~0ull : ((1ull << nb) - 1ull);
             for (int d = 0; d < 2; ++d) {
@@ -236,112 +311,51 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             }
         }
     }
-    STO_CLK(0)
-    enum { PH_OB = 0, PH_SB = 1, PH_OF = 2, PH_SF = 3, PH_FOLD = 4 };
-    int phase = PH_OB;
-    int nliveB = active ? N : 0, nliveF = active ? N : 0;  // original rows with a running backward / forward front
-    int nlistB = 0, nlistF = 0;                             // live re-spawned fronts per direction
-    int wlistB = 0, wlistF = 0;                             // compacted lengths after this iteration's passes
-    int nnew = 0, s = 0, iters = 0;
+    int nliveB = active ? N : 0, nliveF = active ? N : 0;
+    int nB = 0, nF = 0;  // live re-spawned fronts per direction
+    int s = 0, iters = 0;
     int64_t steps = 0;
-    // cursor over original rows: word w, its live bits L, the bits still needing attention, the bits already passed
-    int w = 0, start = 0;
-    u64 L = 0, att = 0, donemask = 0, cur_bit = 0;
-    bool word_open = false;
-    // cursor over a re-spawned list: read index r, write index wr
-    int r = 0, wr = 0, cur_iv = 0;
-    bool finished = !active;
     for (;;) {
-        bool pending = false, fwd = false;
-        int p = 0, q = 0;
-        while (!finished && !pending) {
-            if (phase == PH_OB || phase == PH_OF) {
-                const int d = (phase == PH_OF) ? 1 : 0;
-                if (!word_open) {
-                    if ((d ? nliveF : nliveB) == 0 || w >= NW) { ++phase; r = 0; wr = 0; w = 0; continue; }
-                    L = C.live(d).word(w);
-                    if (!L) { ++w; continue; }
-#if defined(STO_HOSTSIM_COUNTERS)
-                    ++g_memo_words[d];
-#endif
-                    steps += popc64(L);
-                    start = d ? (64 * w + s) : (64 * w - s);  // row i = 64 w + t sits at sample (i -/+ s) mod N
-                    if (start >= N) start -= N;
-                    if (start < 0) start += N;
-                    att = L & ~C.cont(d).window(start);       // fronts that are not on a known-clean edge
-                    donemask = 0;
-                    word_open = true;
-                }
-                if (!att) { C.live(d).set_word(w, L); ++w; word_open = false; continue; }
-                const int t = ctz64(att);
-                cur_bit = 1ull << t;
-                donemask |= cur_bit | (cur_bit - 1ull);
-                const int i = 64 * w + t;
-                p = d ? i + s : i - s;
-                if (p >= N) p -= N;
-                if (p < 0) p += N;
-                if (C.stop(d).test(p)) { L &= ~cur_bit; if (d) --nliveF; else --nliveB; att &= ~donemask; continue; }
-                q = d ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-                fwd = d != 0;
-                pending = true;
-            } else if (phase == PH_SB || phase == PH_SF) {
-                const int d = (phase == PH_SF) ? 1 : 0;
-                int32_t* list = d ? W.spF : W.spB;
-                if (r >= (d ? nlistF : nlistB)) { if (d) wlistF = wr; else wlistB = wr; ++phase; w = 0; word_open = false; continue; }
-                cur_iv = list[at(r, ld, b)];
-                ++r;
-                ++steps;
-                p = d ? cur_iv + s : cur_iv - s;
-                if (p >= N) p -= N;
-                if (p < 0) p += N;
-                if (C.cont(d).test(p)) { list[at(wr, ld, b)] = cur_iv; ++wr; continue; }
-                if (C.stop(d).test(p)) continue;  // the front stops here: dropped from the list
-                q = d ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-                fwd = d != 0;
-                pending = true;
-            } else {  // PH_FOLD: append the rows spawned in this iteration behind both lists (simulator.py:351-356)
-                if (wlistF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
-                for (int j = 0; j < nnew; ++j) {
-                    const int ivb = W.spB[at(nlistB + j, ld, b)];     // (q + s + 1) mod N
-                    int ivf = (ivb - 2 * (s + 1)) % N;                 // (q - (s + 1)) mod N
-                    if (ivf < 0) ivf += N;
-                    W.spB[at(wlistB + j, ld, b)] = ivb;
-                    W.spF[at(wlistF + j, ld, b)] = ivf;
-                }
-                nlistB = wlistB + nnew;
-                nlistF = wlistF + nnew;
-                nnew = 0;
-                s = (s + 1 == N) ? 0 : s + 1;
-                ++iters;
-                if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
-                finished = (nliveB == 0 && nliveF == 0 && nlistB == 0 && nlistF == 0) || status != 0;
-                phase = PH_OB;
-                w = 0;
-                word_open = false;
-            }
-        }
+        const bool done = (nliveB == 0 && nliveF == 0 && nB == 0 && nF == 0) || status != 0;
+        if (warp_all(done)) break;
+        int nnew = 0;
+        STO_CLK(0)
+        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status);
         STO_CLK(1)
-        if (warp_all(finished)) break;
-        if (pending) {
-            bool spawn, changed;
-            const bool stopped = memo_step(A, C, V, b, fwd, p, q, lat0, status, spawn, changed);
-            const int d = fwd ? 1 : 0;
-            if (spawn) memo_spawn(A, W, b, q, s, nlistB, nnew, status);
-            if (phase == PH_OB || phase == PH_OF) {
-                if (stopped) { L &= ~cur_bit; if (d) --nliveF; else --nliveB; }
-                // later rows of this word may now face a dirty edge: re-read the window after a state change
-                att = changed ? (L & ~C.cont(d).window(start) & ~donemask) : (att & ~donemask);
-            } else if (!stopped) {
-                int32_t* list = d ? W.spF : W.spB;
-                list[at(wr, ld, b)] = cur_iv;
-                ++wr;
-            }
-            if (status != 0) finished = true;
-        }
+        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);
         STO_CLK(2)
+        {
+            int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
+            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status);
+        }
+        STO_CLK(3)
+        int wF;
+        {
+            int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
+            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status);
+        }
+        STO_CLK(4)
+        if (!done) {
+            // fold the rows spawned in this iteration behind both lists (simulator.py:351-356)
+            if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
+            for (int j = 0; j < nnew; ++j) {
+                const int ivb = W.spB[at(nB + j, ld, b)];   // (q + s + 1) mod N
+                int ivf = (ivb - 2 * (s + 1)) % N;            // (q - (s + 1)) mod N
+                if (ivf < 0) ivf += N;
+                W.spB[at(wB + j, ld, b)] = ivb;
+                W.spF[at(wF + j, ld, b)] = ivf;
+            }
+            nB = wB + nnew;
+            nF = wF + nnew;
+            s = (s + 1 == N) ? 0 : s + 1;
+            ++iters;
+            if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
+        }
+        STO_CLK(5)
     }
+    STO_CLK(6)
     if (active) qss_finish(A, b, status, steps, iters);
-    STO_CLK(3)
+    STO_CLK(7)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];
 #endif
