@@ -49,6 +49,8 @@ typedef unsigned long long u64;
 #if defined(STO_HOSTSIM_COUNTERS)
 static long long g_memo_evals[2] = {0, 0};   // host-side test instrumentation only
 static long long g_memo_words[2] = {0, 0};
+static long long g_sp_visits[2] = {0, 0}, g_sp_distinct[2] = {0, 0}, g_sp_on_live_orig[2] = {0, 0};
+static long long g_sp_evals[2] = {0, 0}, g_sp_changed[2] = {0, 0}, g_sp_maxlist[2] = {0, 0};
 #endif
 
 STO_HD int ctz64(u64 x) {
@@ -205,52 +207,69 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
 #define STO_CLK(k)
 #endif
 
-// One sub-pass over the original rows, all lanes of the warp walking the same 64-row word together (the plane
-// words of the 32 candidates sit side by side in shared memory).  s = (k-1) mod N.
+// Both walkers below are "decoupled search, convergent evaluation": every lane advances through ITS OWN fronts
+// (shared-memory tests only) until it finds one that needs an FP64 evaluation; then the warp evaluates one step for
+// every lane that has one.  A warp so needs max_lane(#evaluations) rounds per sub-pass - not one round per
+// (word, bit) or list slot in which ANY lane has work, which is what a slot-aligned lock-step walk costs (with 11 %
+// of the re-spawned fronts needing an evaluation, 97 % of the slots of a 32-lane warp do; profiles/r01_*).
+
+// One sub-pass over the original rows.  s = (k-1) mod N.
 template <bool FWD>
 STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                                int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive,
                                int64_t& steps, int& status) {
-    const int N = A.N, d = FWD ? 1 : 0;
+    const int N = A.N, NW = W.W, d = FWD ? 1 : 0;
     const Ring live = C.live(d), cont = C.cont(d), stop = C.stop(d);
-    for (int w = 0; w < W.W; ++w) {
-        if (skip) continue;
-        u64 L = live.word(w);
-        if (!L) continue;
+    int w = 0, start = 0, p = 0, q = 0;
+    u64 L = 0, att = 0, donemask = 0, bit = 0;
+    bool open = false;
+    for (;;) {
+        bool pending = false;
+        if (!skip) {
+            for (;;) {
+                if (!open) {
+                    if (w >= NW) break;
+                    L = live.word(w);
+                    if (!L) { ++w; continue; }
 #if defined(STO_HOSTSIM_COUNTERS)
-        ++g_memo_words[d];
+                    ++g_memo_words[d];
 #endif
-        steps += popc64(L);
-        // row i = 64 w + t sits at sample (i -/+ s) mod N
-        int start = FWD ? (64 * w + s) : (64 * w - s);
-        if (start >= N) start -= N;
-        if (start < 0) start += N;
-        u64 att = L & ~cont.window(start);  // fronts that are not on a known-clean edge
-        u64 donemask = 0;
-        while (att) {
-            const int t = ctz64(att);
-            const u64 bit = 1ull << t;
-            donemask |= bit | (bit - 1ull);
-            const int i = 64 * w + t;
-            int p = FWD ? i + s : i - s;
-            if (p >= N) p -= N;
-            if (p < 0) p += N;
-            const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-            bool stopped, changed = false, spawn = false;
-            if (stop.test(p)) stopped = true;
-            else stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+                    steps += popc64(L);
+                    start = FWD ? (64 * w + s) : (64 * w - s);  // row i = 64 w + t sits at sample (i -/+ s) mod N
+                    if (start >= N) start -= N;
+                    if (start < 0) start += N;
+                    att = L & ~cont.window(start);              // fronts that are not on a known-clean edge
+                    donemask = 0;
+                    open = true;
+                }
+                if (!att) { live.set_word(w, L); ++w; open = false; continue; }
+                const int t = ctz64(att);
+                bit = 1ull << t;
+                donemask |= bit | (bit - 1ull);
+                p = FWD ? 64 * w + t + s : 64 * w + t - s;
+                if (p >= N) p -= N;
+                if (p < 0) p += N;
+                if (stop.test(p)) { L &= ~bit; --nlive; att &= ~donemask; continue; }
+                q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+                pending = true;
+                break;
+            }
+        }
+        if (!warp_any(pending)) break;
+        if (pending) {
+            bool changed = false, spawn = false;
+            const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
             if (stopped) { L &= ~bit; --nlive; }
             if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
             // later rows of this word may now face a dirty edge: re-read the window after a state change
             att = changed ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
         }
-        live.set_word(w, L);
     }
 }
 
-// One sub-pass over the live re-spawned fronts of one direction (creation order).  The list is compacted in
-// place while it is walked (fronts that stop are dropped); four entries are fetched ahead so the common case -
-// every front on a known-clean edge - costs one overlapped global round trip per four fronts.
+// One sub-pass over the live re-spawned fronts of one direction (creation order).  The list (global memory) is
+// compacted in place while it is walked; four entries are kept in flight ahead of the read cursor so the walk is
+// not a chain of dependent global round trips.
 template <bool FWD>
 STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                              int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
@@ -258,32 +277,50 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
     const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
     const Ring cont = C.cont(d), stop = C.stop(d);
     int32_t* list = FWD ? W.spF : W.spB;
-    const int nmax = warp_max(skip ? 0 : nlist);
-    int w = 0;
-    for (int r0 = 0; r0 < nmax; r0 += 4) {
-        if (skip || r0 >= nlist) continue;
-        int iv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) iv[j] = (r0 + j < nlist) ? list[at(r0 + j, ld, b)] : -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (iv[j] < 0) continue;
-            int p = FWD ? iv[j] + s : iv[j] - s;
-            if (p >= N) p -= N;
-            if (p < 0) p += N;
-            ++steps;
-            bool stopped = false;
-            if (!cont.test(p)) {
-                const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-                bool changed = false, spawn = false;
-                if (stop.test(p)) stopped = true;
-                else stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
-                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
-            }
-            if (!stopped) { list[at(w, ld, b)] = iv[j]; ++w; }
+#if defined(STO_HOSTSIM_COUNTERS)
+    if (!skip) {
+        static std::vector<int> seen; seen.assign(N, 0);
+        const Ring live = C.live(d);
+        g_sp_maxlist[d] += nlist;
+        for (int r = 0; r < nlist; ++r) {
+            int iv = list[at(r, ld, b)];
+            ++g_sp_visits[d];
+            if (!seen[iv]) { seen[iv] = 1; ++g_sp_distinct[d]; if (live.test(iv)) ++g_sp_on_live_orig[d]; }
         }
     }
-    return skip ? nlist : w;
+#endif
+    if (skip) nlist = 0;
+    int r = 0, w = 0, iv = 0, p = 0, q = 0;
+    int f0 = (0 < nlist) ? list[at(0, ld, b)] : -1, f1 = (1 < nlist) ? list[at(1, ld, b)] : -1,
+        f2 = (2 < nlist) ? list[at(2, ld, b)] : -1, f3 = (3 < nlist) ? list[at(3, ld, b)] : -1;
+    for (;;) {
+        bool pending = false;
+        while (r < nlist) {
+            iv = f0; f0 = f1; f1 = f2; f2 = f3;
+            f3 = (r + 4 < nlist) ? list[at(r + 4, ld, b)] : -1;
+            ++r;
+            ++steps;
+            p = FWD ? iv + s : iv - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            if (cont.test(p)) { list[at(w, ld, b)] = iv; ++w; continue; }
+            if (stop.test(p)) continue;  // the front stops here: dropped from the list
+            q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+            pending = true;
+            break;
+        }
+        if (!warp_any(pending)) break;
+        if (pending) {
+            bool changed = false, spawn = false;
+            const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+#if defined(STO_HOSTSIM_COUNTERS)
+            ++g_sp_evals[d]; if (changed) ++g_sp_changed[d];
+#endif
+            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            if (!stopped) { list[at(w, ld, b)] = iv; ++w; }
+        }
+    }
+    return w;
 }
 
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
@@ -322,7 +359,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         STO_CLK(0)
         memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status);
         STO_CLK(1)
-        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);
+        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);  // 0 if done
         STO_CLK(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)

@@ -82,6 +82,12 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
     return 0;
 }
 
+void hostsim_sp_counters(long long* out12, int reset) {
+    long long* src[6] = {sto::g_sp_visits, sto::g_sp_distinct, sto::g_sp_on_live_orig, sto::g_sp_evals, sto::g_sp_changed,
+                         sto::g_sp_maxlist};
+    for (int k = 0; k < 6; ++k) { out12[2 * k] = src[k][0]; out12[2 * k + 1] = src[k][1]; if (reset) src[k][0] = src[k][1] = 0; }
+}
+
 void hostsim_counters(long long* out4, int reset) {
     out4[0] = sto::g_memo_evals[0]; out4[1] = sto::g_memo_evals[1];
     out4[2] = sto::g_memo_words[0]; out4[3] = sto::g_memo_words[1];
