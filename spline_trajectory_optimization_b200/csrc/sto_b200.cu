@@ -80,7 +80,7 @@ struct QssWork {
 constexpr size_t kMemoSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use on sm_100a
 inline int effective_impl(int N, int impl) {
     // the memoised kernel keeps six bit planes per candidate in shared memory: 48 * ceil(N/64) bytes
-    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N && sto::memo_plane_bytes(N) <= kMemoSmemBudget)
+    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N && sto::memo_smem_bytes(N) <= kMemoSmemBudget)
                ? STO_QSS_MEMO : STO_QSS_PLAIN;
 }
 QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool need_state) {
@@ -160,7 +160,7 @@ __global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int lanes, cons
     bool active;
     const int b = candidate_of_thread(lanes, A.B, active);
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
-    unsigned long long* base = sto_planes + (size_t)warp_in_block * 6 * W.W * lanes;
+    unsigned long long* base = sto_planes + (size_t)warp_in_block * (sto::memo_smem_bytes(A.N) / 8) * lanes;
     const sto::MemoCtx C = sto::memo_bind(base, lanes, lane < lanes ? lane : 0, A.N, W.W);
     sto::qss_memo_candidate(A, W, C, V, b, active);
 }
@@ -263,7 +263,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
         else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
-        const size_t per_cand = sto::memo_plane_bytes(A.N);
+        const size_t per_cand = sto::memo_smem_bytes(A.N);
         const int lanes = pick_lanes(A.B, per_cand);
         const int warps = (A.B + lanes - 1) / lanes;
         const size_t smem = per_cand * lanes;  // one warp per CTA

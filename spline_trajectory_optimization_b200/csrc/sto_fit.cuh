@@ -12,6 +12,10 @@
 #pragma once
 #include "sto_common.cuh"
 
+#ifndef STO_FIT_CHUNK
+#define STO_FIT_CHUNK 8
+#endif
+
 namespace sto {
 
 struct FitArgs {
@@ -50,16 +54,28 @@ STO_HD void fit_candidate(const FitArgs& A, int b) {
     fit_point(A, 0, b, x0, y0);
     double xp = x0, yp = y0, acc = 0.0;
     A.u[at(0, ld, b)] = 0.0;
-    for (int i = 1; i <= M; ++i) {
-        double x, y;
-        if (i < M) fit_point(A, i, b, x, y); else { x = x0; y = y0; }  // closed loop (trajectory.py:217-218)
-        double dx = x - xp, dy = y - yp;
-        double dist = 0.0;
-        dist = dist + dx * dx;
-        dist = dist + dy * dy;
-        acc = acc + sqrt(dist);
-        A.u[at(i, ld, b)] = acc;
-        xp = x; yp = y;
+    // Rows are processed in chunks of STO_FIT_CHUNK with all loads of a chunk issued before its (serially
+    // dependent) arithmetic: one exposed memory round trip per chunk instead of one per row.
+    for (int i0 = 1; i0 <= M; i0 += STO_FIT_CHUNK) {
+        double xs[STO_FIT_CHUNK], ys[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int i = i0 + k;
+            if (i < M) fit_point(A, i, b, xs[k], ys[k]); else { xs[k] = x0; ys[k] = y0; }  // closed loop (trajectory.py:217-218)
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int i = i0 + k;
+            if (i <= M) {
+                double dx = xs[k] - xp, dy = ys[k] - yp;
+                double dist = 0.0;
+                dist = dist + dx * dx;
+                dist = dist + dy * dy;
+                acc = acc + sqrt(dist);
+                A.u[at(i, ld, b)] = acc;
+                xp = xs[k]; yp = ys[k];
+            }
+        }
     }
     const double total = acc;
     if (!(total > 0.0)) {  // FITPACK returns ier=10; scipy raises
@@ -80,53 +96,77 @@ STO_HD void fit_candidate(const FitArgs& A, int b) {
     double beta = 0.0, gamma = 0.0, alpha = 0.0;
     double cpp = 0.0, zxp = 0.0, zyp = 0.0, zzp = 0.0;
     double zx_last = 0.0, zy_last = 0.0, zz_last = 0.0;
-    for (int j = 0; j < M; ++j) {
-        double b0 = ((t3 - t2) * (t3 - t2)) / ((t3 - t0) * (t3 - t1));
-        double b2 = ((t2 - t1) * (t2 - t1)) / ((t4 - t1) * (t3 - t1));
-        double b1 = (1.0 - b0) - b2;
-        double pxj, pyj;
-        fit_point(A, j, b, pxj, pyj);
-        double den, ncp, nzx, nzy, nzz;
-        if (j == 0) {
-            beta = b0;       // corner: row 0, column M-1
-            gamma = -b1;
-            den = b1 - gamma;
-            ncp = b2 / den;
-            nzx = pxj / den;
-            nzy = pyj / den;
-            nzz = gamma / den;
-        } else {
-            double dj = b1, wj = 0.0;
-            if (j == M - 1) {
-                alpha = b2;  // corner: row M-1, column 0
-                dj = b1 - alpha * beta / gamma;
-                wj = alpha;
-            }
-            den = dj - b0 * cpp;
-            ncp = b2 / den;
-            nzx = (pxj - b0 * zxp) / den;
-            nzy = (pyj - b0 * zyp) / den;
-            nzz = (wj - b0 * zzp) / den;
+    for (int j0 = 0; j0 < M; j0 += STO_FIT_CHUNK) {
+        double pxs[STO_FIT_CHUNK], pys[STO_FIT_CHUNK], tn[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            if (j < M) { fit_point(A, j, b, pxs[k], pys[k]); tn[k] = fit_knot(A, j + 3, b); }
+            else { pxs[k] = pys[k] = tn[k] = 0.0; }
         }
-        A.cp[at(j, ld, b)] = ncp;
-        A.zx[at(j, ld, b)] = nzx;
-        A.zy[at(j, ld, b)] = nzy;
-        A.zz[at(j, ld, b)] = nzz;
-        cpp = ncp; zxp = nzx; zyp = nzy; zzp = nzz;
-        t0 = t1; t1 = t2; t2 = t3; t3 = t4;
-        t4 = fit_knot(A, j + 3, b);
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            if (j >= M) break;
+            double b0 = ((t3 - t2) * (t3 - t2)) / ((t3 - t0) * (t3 - t1));
+            double b2 = ((t2 - t1) * (t2 - t1)) / ((t4 - t1) * (t3 - t1));
+            double b1 = (1.0 - b0) - b2;
+            const double pxj = pxs[k], pyj = pys[k];
+            double den, ncp, nzx, nzy, nzz;
+            if (j == 0) {
+                beta = b0;       // corner: row 0, column M-1
+                gamma = -b1;
+                den = b1 - gamma;
+                ncp = b2 / den;
+                nzx = pxj / den;
+                nzy = pyj / den;
+                nzz = gamma / den;
+            } else {
+                double dj = b1, wj = 0.0;
+                if (j == M - 1) {
+                    alpha = b2;  // corner: row M-1, column 0
+                    dj = b1 - alpha * beta / gamma;
+                    wj = alpha;
+                }
+                den = dj - b0 * cpp;
+                ncp = b2 / den;
+                nzx = (pxj - b0 * zxp) / den;
+                nzy = (pyj - b0 * zyp) / den;
+                nzz = (wj - b0 * zzp) / den;
+            }
+            A.cp[at(j, ld, b)] = ncp;
+            A.zx[at(j, ld, b)] = nzx;
+            A.zy[at(j, ld, b)] = nzy;
+            A.zz[at(j, ld, b)] = nzz;
+            cpp = ncp; zxp = nzx; zyp = nzy; zzp = nzz;
+            t0 = t1; t1 = t2; t2 = t3; t3 = t4;
+            t4 = tn[k];
+        }
     }
     zx_last = zxp; zy_last = zyp; zz_last = zzp;
     // pass 4: back substitution
     double zxn = zx_last, zyn = zy_last, zzn = zz_last;
-    for (int j = M - 2; j >= 0; --j) {
-        double c = A.cp[at(j, ld, b)];
-        zxn = A.zx[at(j, ld, b)] - c * zxn;
-        zyn = A.zy[at(j, ld, b)] - c * zyn;
-        zzn = A.zz[at(j, ld, b)] - c * zzn;
-        A.zx[at(j, ld, b)] = zxn;
-        A.zy[at(j, ld, b)] = zyn;
-        A.zz[at(j, ld, b)] = zzn;
+    for (int j0 = M - 2; j0 >= 0; j0 -= STO_FIT_CHUNK) {
+        double cs[STO_FIT_CHUNK], xs[STO_FIT_CHUNK], ys[STO_FIT_CHUNK], zs[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            if (j >= 0) {
+                cs[k] = A.cp[at(j, ld, b)]; xs[k] = A.zx[at(j, ld, b)];
+                ys[k] = A.zy[at(j, ld, b)]; zs[k] = A.zz[at(j, ld, b)];
+            } else { cs[k] = xs[k] = ys[k] = zs[k] = 0.0; }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            if (j < 0) break;
+            zxn = xs[k] - cs[k] * zxn;
+            zyn = ys[k] - cs[k] * zyn;
+            zzn = zs[k] - cs[k] * zzn;
+            A.zx[at(j, ld, b)] = zxn;
+            A.zy[at(j, ld, b)] = zyn;
+            A.zz[at(j, ld, b)] = zzn;
+        }
     }
     // pass 5: Sherman-Morrison correction, e -> c with the one-slot rotation and the periodic wrap
     double denom = (1.0 + zzn) + beta * zz_last / gamma;

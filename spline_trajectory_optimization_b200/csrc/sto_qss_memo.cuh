@@ -106,14 +106,24 @@ struct Ring {
 struct MemoCtx {
     u64* base;
     int stride, N, W;
+    int32_t* ring;  // shared-memory prefetch ring of this lane for the re-spawned lists: slot k at ring[k * stride]
     STO_HD Ring plane(int k) const { return Ring{base + (size_t)k * W * stride, stride, N, W}; }
     STO_HD Ring live(int d) const { return plane(0 + d); }   // d = 0 backward (edge p -> p-1), 1 forward (p -> p+1)
     STO_HD Ring cont(int d) const { return plane(2 + d); }
     STO_HD Ring stop(int d) const { return plane(4 + d); }
 };
 
+#ifndef STO_LIST_RING
+#define STO_LIST_RING 16  // entries in flight ahead of the list cursor (power of two)
+#endif
+
+// Shared memory per candidate: six bit planes + the list prefetch ring.
+STO_HD size_t memo_smem_bytes(int N) { return memo_plane_bytes(N) + STO_LIST_RING * sizeof(int32_t); }
+
+// base: [6 planes][W words][stride lanes] u64, followed by [STO_LIST_RING][stride] int32.
 STO_HD MemoCtx memo_bind(u64* base, int stride, int lane, int N, int W) {
-    return MemoCtx{base + lane, stride, N, W};
+    int32_t* ring = reinterpret_cast<int32_t*>(base + (size_t)6 * W * stride) + lane;
+    return MemoCtx{base + lane, stride, N, W, ring};
 }
 
 // The stored state of sample j changed: forget every memo that read it.
@@ -201,10 +211,26 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
     ++nnew;
 }
 
+
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
 #define STO_CLK(k) { long long c_ = clock64(); dbg_acc[k] += c_ - dbg_t; dbg_t = c_; }
+#define STO_SUBCLK_DECL long long sub_t = clock64();
+#define STO_SUBCLK(k) { long long c_ = clock64(); g_sub[k] += c_ - sub_t; sub_t = c_; }
+#define STO_SUBCNT(k) { g_sub[k] += 1; }
 #else
 #define STO_CLK(k)
+#define STO_SUBCLK_DECL
+#define STO_SUBCLK(k)
+#define STO_SUBCNT(k)
+#endif
+#if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+// per-thread sub-phase accumulators (profiling build only): [0,1] orig search/eval clocks, [2,3] spawned search/eval
+// clocks, [4,5] orig/spawned evaluation rounds, [6] warp rounds of spawned, [7] warp rounds of orig
+#define STO_SUB_PARAM , long long* g_sub
+#define STO_SUB_ARG , g_sub
+#else
+#define STO_SUB_PARAM
+#define STO_SUB_ARG
 #endif
 
 // Both walkers below are "decoupled search, convergent evaluation": every lane advances through ITS OWN fronts
@@ -217,8 +243,9 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
 template <bool FWD>
 STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                                int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive,
-                               int64_t& steps, int& status) {
+                               int64_t& steps, int& status STO_SUB_PARAM) {
     const int N = A.N, NW = W.W, d = FWD ? 1 : 0;
+    STO_SUBCLK_DECL
     const Ring live = C.live(d), cont = C.cont(d), stop = C.stop(d);
     int w = 0, start = 0, p = 0, q = 0;
     u64 L = 0, att = 0, donemask = 0, bit = 0;
@@ -255,8 +282,11 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                 break;
             }
         }
+        STO_SUBCLK(0)
         if (!warp_any(pending)) break;
+        STO_SUBCNT(7)
         if (pending) {
+            STO_SUBCNT(4)
             bool changed = false, spawn = false;
             const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
             if (stopped) { L &= ~bit; --nlive; }
@@ -264,6 +294,7 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             // later rows of this word may now face a dirty edge: re-read the window after a state change
             att = changed ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
         }
+        STO_SUBCLK(1)
     }
 }
 
@@ -273,10 +304,11 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
 template <bool FWD>
 STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                              int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
-                             int& status) {
+                             int& status STO_SUB_PARAM) {
     const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
     const Ring cont = C.cont(d), stop = C.stop(d);
     int32_t* list = FWD ? W.spF : W.spB;
+    STO_SUBCLK_DECL
 #if defined(STO_HOSTSIM_COUNTERS)
     if (!skip) {
         static std::vector<int> seen; seen.assign(N, 0);
@@ -291,13 +323,32 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
 #endif
     if (skip) nlist = 0;
     int r = 0, w = 0, iv = 0, p = 0, q = 0;
-    int f0 = (0 < nlist) ? list[at(0, ld, b)] : -1, f1 = (1 < nlist) ? list[at(1, ld, b)] : -1,
-        f2 = (2 < nlist) ? list[at(2, ld, b)] : -1, f3 = (3 < nlist) ? list[at(3, ld, b)] : -1;
+    // Prefetch ring: list entries r .. r+RING-1 are copied global -> shared with cp.async (no register dependency,
+    // so the walk never waits on an entry that was requested RING visits earlier); one commit group per entry.
+#if defined(__CUDA_ARCH__)
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(C.ring);
+#pragma unroll 1
+    for (int k = 0; k < STO_LIST_RING; ++k) {
+        if (k < nlist)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)(k * C.stride)),
+                         "l"(list + at(k, ld, b)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
     for (;;) {
         bool pending = false;
         while (r < nlist) {
-            iv = f0; f0 = f1; f1 = f2; f2 = f3;
-            f3 = (r + 4 < nlist) ? list[at(r + 4, ld, b)] : -1;
+#if defined(__CUDA_ARCH__)
+            asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");
+            const int slot = (r & (STO_LIST_RING - 1)) * C.stride;
+            iv = C.ring[slot];
+            if (r + STO_LIST_RING < nlist)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
+                             "l"(list + at(r + STO_LIST_RING, ld, b)) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+            iv = list[at(r, ld, b)];
+#endif
             ++r;
             ++steps;
             p = FWD ? iv + s : iv - s;
@@ -309,8 +360,11 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             pending = true;
             break;
         }
+        STO_SUBCLK(2)
         if (!warp_any(pending)) break;
+        STO_SUBCNT(6)
         if (pending) {
+            STO_SUBCNT(5)
             bool changed = false, spawn = false;
             const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
 #if defined(STO_HOSTSIM_COUNTERS)
@@ -319,6 +373,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
             if (!stopped) { list[at(w, ld, b)] = iv; ++w; }
         }
+        STO_SUBCLK(3)
     }
     return w;
 }
@@ -330,6 +385,8 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
     const double lat0 = max_lat_acc(V, 0.0);
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long g_sub_store[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long* g_sub = g_sub_store;
     long long dbg_t = clock64();
 #endif
     int status = 0;
@@ -357,19 +414,19 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
-        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status);
+        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status STO_SUB_ARG);
         STO_CLK(1)
-        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status);  // 0 if done
+        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
-            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status);
+            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status STO_SUB_ARG);
         }
         STO_CLK(3)
         int wF;
         {
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
-            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status);
+            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
         }
         STO_CLK(4)
         if (!done) {
@@ -395,6 +452,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
     STO_CLK(7)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];
+    if (active && A.lat) for (int k = 0; k < 8; ++k) A.lat[at(k, ld, b)] = (double)g_sub[k];   // profiling build only
 #endif
 }
 

@@ -32,7 +32,7 @@ for _ in range(2):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = run_qss(S["x"], S["y"], S["radius"], ev.vehicle, B=B, impl=_lib.QSS_MEMO, profiles=False)
+    res = run_qss(S["x"], S["y"], S["radius"], ev.vehicle, B=B, impl=_lib.QSS_MEMO, profiles=True)
     e1.record()
     torch.cuda.synchronize()
     print("qss ms (incl. chord kernel)", e0.elapsed_time(e1))
@@ -43,3 +43,8 @@ tot = summ.sum(axis=0)
 print("per-thread total clocks: mean %.3g  (%.1f ms at 1.965 GHz)" % (tot.mean(), tot.mean() / 1.965e6))
 for k, n in enumerate(names):
     print("%-18s %6.2f %%   mean clocks %.3g" % (n, 100 * summ[k].mean() / tot.mean(), summ[k].mean()))
+sub = res["lat_acc"][:8, :B].cpu().numpy()
+subn = ["orig search clk", "orig eval clk", "spawned search clk", "spawned eval clk", "orig evals (lane)", "spawned evals (lane)",
+        "spawned warp rounds", "orig warp rounds"]
+for k, n in enumerate(subn):
+    print("%-22s mean %.4g   max %.4g" % (n, sub[k].mean(), sub[k].max()))
