@@ -242,7 +242,7 @@ STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s,
 // One sub-pass over the original rows.  s = (k-1) mod N.
 template <bool FWD>
 STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                               int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive,
+                               int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive, u64& words,
                                int64_t& steps, int& status STO_SUB_PARAM) {
     const int N = A.N, NW = W.W, d = FWD ? 1 : 0;
     STO_SUBCLK_DECL
@@ -250,14 +250,22 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
     int w = 0, start = 0, p = 0, q = 0;
     u64 L = 0, att = 0, donemask = 0, bit = 0;
     bool open = false;
+    // `words` (tracks of <= 4096 samples): one bit per 64-row word that still holds a running front, so the walk
+    // visits only those (late in a run that is a handful of the W words).  Longer tracks scan every word.
+    const bool use_mask = NW <= 64;
+    u64 todo = use_mask ? words : 0ull;
     for (;;) {
         bool pending = false;
         if (!skip) {
             for (;;) {
                 if (!open) {
-                    if (w >= NW) break;
+                    if (use_mask) {
+                        if (!todo) break;
+                        w = ctz64(todo);
+                        todo &= todo - 1ull;
+                    } else if (w >= NW) break;
                     L = live.word(w);
-                    if (!L) { ++w; continue; }
+                    if (!L) { if (use_mask) words &= ~(1ull << w); else ++w; continue; }
 #if defined(STO_HOSTSIM_COUNTERS)
                     ++g_memo_words[d];
 #endif
@@ -269,7 +277,12 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                     donemask = 0;
                     open = true;
                 }
-                if (!att) { live.set_word(w, L); ++w; open = false; continue; }
+                if (!att) {
+                    live.set_word(w, L);
+                    if (use_mask) { if (!L) words &= ~(1ull << w); } else ++w;
+                    open = false;
+                    continue;
+                }
                 const int t = ctz64(att);
                 bit = 1ull << t;
                 donemask |= bit | (bit - 1ull);
@@ -354,7 +367,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             p = FWD ? iv + s : iv - s;
             if (p >= N) p -= N;
             if (p < 0) p += N;
-            if (cont.test(p)) { list[at(w, ld, b)] = iv; ++w; continue; }
+            if (cont.test(p)) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; continue; }
             if (stop.test(p)) continue;  // the front stops here: dropped from the list
             q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
             pending = true;
@@ -371,7 +384,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             ++g_sp_evals[d]; if (changed) ++g_sp_changed[d];
 #endif
             if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
-            if (!stopped) { list[at(w, ld, b)] = iv; ++w; }
+            if (!stopped) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; }
         }
         STO_SUBCLK(3)
     }
@@ -406,6 +419,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         }
     }
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
+    u64 wordsB = (W.W >= 64) ? ~0ull : ((1ull << W.W) - 1ull), wordsF = wordsB;  // words with running fronts
     int nB = 0, nF = 0;  // live re-spawned fronts per direction
     int s = 0, iters = 0;
     int64_t steps = 0;
@@ -414,13 +428,13 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
-        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, steps, status STO_SUB_ARG);
+        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
         STO_CLK(1)
         const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
-            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, steps, status STO_SUB_ARG);
+            memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status STO_SUB_ARG);
         }
         STO_CLK(3)
         int wF;
