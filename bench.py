@@ -205,19 +205,13 @@ def run_gpu_arm(args):
     ld = d_off[0].shape[1]
     lap = torch.empty(ld, dtype=torch.float64, device=dev)
     st = torch.empty(ld, dtype=torch.int32, device=dev)
-    pair = torch.empty(2, dtype=torch.float64, device=dev)
-    gathered = torch.empty(2 * world, dtype=torch.float64, device=dev)
+    from spline_trajectory_optimization_b200 import sharding
 
     def step(j):
         l, s = ev.lap_times(d_off[j & 1], B=B, out=lap, status=st)
         best, idx = ev.argmin(l, s)
-        if world > 1:   # the path's only exchange: (best lap, global candidate index) per rank, then argmin again
-            pair[0] = best[0]
-            pair[1] = (idx[0] + rank * B).to(torch.float64)
-            dist.all_gather_into_tensor(gathered, pair)
-            k = torch.argmin(gathered[0::2])
-            return gathered[2 * k], gathered[2 * k + 1]
-        return best[0], idx[0]
+        # the path's only exchange: one (best lap, global candidate index) pair per rank, then argmin again
+        return sharding.global_argmin(best, idx, rank * B)
 
     def barrier():
         if world > 1:

@@ -11,13 +11,20 @@
 // and clear the four memos that depend on a sample whenever its stored state changes (edges p->p-1, p+1->p,
 // p->p+1, p-1->p).  An infeasible backward step (re-init + spawn, :238-254) is never memoised.
 //
-// Original rows are bit sets over row index (one live backward and one live forward front per row; the
-// front of row i sits at sample i -/+ (k-1) mod N at outer iteration k), memos are bit sets over sample
-// index, and one 64-row word of fronts is matched against the memos with a ring-shifted window - so the
-// ~95 % clean crossings cost a few integer instructions per 64 rows instead of a ~400-instruction FP64
-// evaluation each.  Processing order inside a word is ascending row index with the windows re-read after
-// every state change, which preserves the reference's sequential (Gauss-Seidel) forward sweep exactly.
-// Re-spawned rows keep their explicit table and creation order as in the plain kernel.
+// Data structures (one candidate per lane):
+//   * six bit planes over the N samples / rows in SHARED memory (live fronts B/F by row, CONT and STOP memos B/F by
+//     sample), a private column per lane: a memo test or update is an LDS/STS, not a global round trip;
+//   * original rows: the front of row i sits at sample i -/+ (k-1) mod N at outer iteration k, so a 64-row word of
+//     live fronts is matched against the memo planes with one ring-shifted window; clean crossings cost a few
+//     integer instructions per 64 rows;
+//   * re-spawned rows: two compact lists (global memory) of VIRTUAL ROW indices in creation order, compacted in
+//     place as they are walked, read through a cp.async prefetch ring in shared memory;
+//   * speed / acceleration state v, a and the static chord / radius arrays stay sample-major in global memory.
+// Control: the 32 lanes of a warp move through (outer iteration, sub-pass) together, but inside a sub-pass every
+// lane searches ITS OWN next front that needs an evaluation and the warp then evaluates one step for all lanes at
+// once (divisions, square roots and the scattered state loads always run convergent).  Row order inside a
+// sub-pass is ascending row index with the memo window re-read after every state change, which preserves the
+// reference's sequential (Gauss-Seidel) forward sweep and its Jacobi-with-seam backward sweep exactly.
 #pragma once
 #include "sto_common.cuh"
 #include "sto_qss.cuh"
