@@ -235,3 +235,60 @@ def test_full_size_properties(sto):
     evp = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()), impl="plain")
     lap_plain, _ = evp.lap_times(evp.to_sample_major(torch.from_numpy(off[:256]).cuda()), B=256)
     assert np.array_equal(lap_plain.cpu().numpy(), lap[:256])
+
+
+def test_fused_banked_oval(sto):
+    """BASELINE config 4 (bank-aware QSS through the fused path): synthetic banked oval, 4-column centre line, bank
+    carried to the samples by index; bit-exact against the oracle."""
+    from spline_trajectory_optimization_b200 import candidates
+    from spline_trajectory_optimization_b200.models.race_track import RaceTrack
+    from spline_trajectory_optimization_b200.models.trajectory import Trajectory
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    centre, left, right = candidates.banked_oval(straight=300.0, radius=120.0, spacing=10.0)
+    rt = RaceTrack("oval", left, right, centre, s=1.0, interval=4.0)
+    M = len(rt.center_d)
+    bank = rt.center_d[:, Trajectory.BANK]
+    assert bank.max() > 0.1 and bank.min() >= 0.0
+    B = 37
+    off = candidates.smooth_offsets(M, B, rt.dist_to_left, rt.dist_to_right, seed=5)
+    veh = Vehicle(test_vehicle_params())
+    nrm = rt.left_normals()
+    laps = {}
+    for impl in ("plain", "memo"):
+        ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), veh, bank=bank, impl=impl)
+        lap, st = ev.lap_times(to_sm(off), B=B)
+        assert not st.cpu().numpy().any()
+        laps[impl] = lap.cpu().numpy()
+    g = golden("cand_m579_n579")
+    ov = O.make_vehicle(*veh_args(g))
+    olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
+                            np.sin(bank), ov, n_threads=4, ref_pow=0)
+    assert np.array_equal(laps["plain"], olap) and np.array_equal(laps["memo"], olap)
+    # banking matters: the same lines on the flat track are faster (reference sign quirk, SURVEY.md section 3.4)
+    ev0 = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), veh, bank=None)
+    lap0, _ = ev0.lap_times(to_sm(off), B=B)
+    assert (lap0.cpu().numpy() < laps["memo"]).all()
+
+
+def test_long_track_quarter_metre(sto):
+    """BASELINE config 5 geometry (Monza at 0.25 m: M = N = 23,160; ~25 M front steps per line in the reference): four
+    candidates through the fused path, bit-exact against the oracle.  Exercises multi-word rings (362 words), the
+    reduced candidates-per-warp launch and a 23 k-row Thomas solve."""
+    from spline_trajectory_optimization_b200 import candidates, tracks
+    from spline_trajectory_optimization_b200.models.race_track import RaceTrack
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    c, l, r = tracks.monza_raw()
+    rt = RaceTrack("monza", l, r, c, s=10.0, interval=0.25)
+    M = len(rt.center_d)
+    assert 23000 < M < 23300
+    B = 4
+    off = candidates.smooth_offsets(M, B, rt.dist_to_left, rt.dist_to_right, seed=11)
+    nrm = rt.left_normals()
+    ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
+    lap, st = ev.lap_times(to_sm(off), B=B)
+    lap = lap.cpu().numpy()
+    assert not st.cpu().numpy().any()
+    g = golden("cand_m579_n579")
+    olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
+                            np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=4, ref_pow=0)
+    assert not ost.any() and np.array_equal(lap, olap)
