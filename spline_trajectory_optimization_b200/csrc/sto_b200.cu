@@ -71,7 +71,7 @@ FitWork carve_fit(Carver& c, int M, size_t ld) {
 }
 
 struct QssWork {
-    double *dd, *df, *v, *a;
+    double *dd, *df, *v, *a, *rec;
     uint8_t *rowflag, *sp_flag;
     int32_t *sp_ent, *sp_ext, *sp_turn;
     sto::MemoWork memo;
@@ -91,10 +91,11 @@ QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool 
         w.dd = c.take<double>((size_t)N * ld);
         w.df = c.take<double>((size_t)N * ld);
     }
-    if (need_state) {
+    if (need_state && impl == STO_QSS_PLAIN) {
         w.v = c.take<double>((size_t)N * ld);
         w.a = c.take<double>((size_t)N * ld);
     }
+    if (impl == STO_QSS_MEMO) w.rec = c.take<double>((size_t)N * ld * 4);
     if (impl == STO_QSS_PLAIN) {
         w.rowflag = c.take<uint8_t>((size_t)N * ld);
         w.sp_flag = c.take<uint8_t>((size_t)w.cap * ld);
@@ -383,8 +384,9 @@ int sto_qss_f64(const double* x, const double* y, const double* radius, const do
     if ((size_t)ld != wld) return fail(STO_ERR_INVALID, "sto_qss_f64 needs ld == round_up(B, 32)");
     sto::QssArgs A{};
     A.dd = w.dd; A.df = w.df; A.R = Rw; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = (int)wld; A.cap = w.cap;
-    A.v = (out && out->speed) ? out->speed : w.v;
+    A.v = (out && out->speed) ? out->speed : w.v;      // memo kernel: outputs only (NULL = not materialised)
     A.a = (out && out->lon_acc) ? out->lon_acc : w.a;
+    A.rec = w.rec;
     A.rowflag = w.rowflag; A.sp_ent = w.sp_ent; A.sp_ext = w.sp_ext; A.sp_turn = w.sp_turn; A.sp_flag = w.sp_flag;
     A.owner = out ? out->owner : nullptr;
     A.lat = out ? out->lat_acc : nullptr;
@@ -452,7 +454,7 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     stage_mark(3, st);
     sto::QssArgs A{};
     A.dd = w.qss.dd; A.df = w.qss.df; A.R = w.R; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = ld; A.cap = w.qss.cap;
-    A.v = w.qss.v; A.a = w.qss.a; A.rowflag = w.qss.rowflag;
+    A.v = w.qss.v; A.a = w.qss.a; A.rec = w.qss.rec; A.rowflag = w.qss.rowflag;
     A.sp_ent = w.qss.sp_ent; A.sp_ext = w.qss.sp_ext; A.sp_turn = w.qss.sp_turn; A.sp_flag = w.qss.sp_flag;
     A.lap = lap; A.status = status;
     int rc = launch_qss(A, w.qss, vehicle, impl, false, st);

@@ -32,7 +32,8 @@ struct QssArgs {
     const double* sinb;         // [N] sin(bank) or NULL
     int N, B, ld;
     int cap;                    // capacity of the re-spawned row table (rows per candidate)
-    double *v, *a;              // [N][ld] state (also the SPEED / LON_ACC outputs)
+    double *v, *a;              // [N][ld] state (also the SPEED / LON_ACC outputs); memo kernel: optional outputs
+    double* rec;                // memo kernel only: [B][N] records {v, a, dd, R} (32 B, CANDIDATE-major, see StateRec)
     uint8_t* rowflag;           // [N][ld] bit0 = backward front stopped, bit1 = forward front stopped
     int32_t *sp_ent, *sp_ext, *sp_turn;  // [cap][ld] re-spawned rows
     uint8_t* sp_flag;           // [cap][ld]
@@ -104,14 +105,32 @@ STO_HD bool row_step(const QssArgs& A, const sto_vehicle_f64& V, int b, int p, i
     return true;
 }
 
+// Where a kernel keeps (v, a, R) of one candidate: sample-major arrays (plain kernel) ...
+struct StateSoA {
+    const QssArgs& A;
+    int b;
+    STO_HD double v(int i) const { return A.v[at(i, A.ld, b)]; }
+    STO_HD double a(int i) const { return A.a[at(i, A.ld, b)]; }
+    STO_HD double R(int i) const { return A.R[at(i, A.ld, b)]; }
+};
+// ... or candidate-major 32-byte records {v, a, dd, R} (memoised kernel): the two samples an evaluation touches are
+// adjacent in memory (one 128-byte line 3 times out of 4) instead of six sectors in six different arrays.
+struct StateRec {
+    const double* rec;  // this candidate's N records
+    STO_HD double v(int i) const { return rec[4 * (size_t)i + 0]; }
+    STO_HD double a(int i) const { return rec[4 * (size_t)i + 1]; }
+    STO_HD double R(int i) const { return rec[4 * (size_t)i + 3]; }
+};
+
 // fill_time + lap + summary (trajectory.py:158-180, simulator.py:375-386)
-STO_HD void qss_finish(const QssArgs& A, int b, int status, int64_t steps, int iters) {
+template <class State>
+STO_HD void qss_finish(const QssArgs& A, const State& S, bool write_va, int b, int status, int64_t steps, int iters) {
     const int N = A.N, ld = A.ld;
     double lap = 0.0, t0 = 0.0;
     double vmin = 0.0, vmaxs = 0.0, latmax = 0.0, amax = 0.0, amin = 0.0;
     if (status == 0) {
-        const double v0 = A.v[at(0, ld, b)];
-        double vprev = A.v[at(N - 1, ld, b)];
+        const double v0 = S.v(0);
+        double vprev = S.v(N - 1);
         t0 = A.df[at(N - 1, ld, b)] / (0.5 * (vprev + v0));  // TIME[0] = closing segment
         if (A.tseg) A.tseg[at(0, ld, b)] = t0;
         lap = lap + t0;
@@ -119,9 +138,13 @@ STO_HD void qss_finish(const QssArgs& A, int b, int status, int64_t steps, int i
         bool bad = !(t0 == t0);
         for (int i = 0; i < N; ++i) {
             const double vi = vprev;
-            const double ai = A.a[at(i, ld, b)];
-            const double li = calc_lat(vi, A.R[at(i, ld, b)], gsb_at(A, i));
+            const double ai = S.a(i);
+            const double li = calc_lat(vi, S.R(i), gsb_at(A, i));
             if (A.lat) A.lat[at(i, ld, b)] = li;
+            if (write_va) {
+                if (A.v) A.v[at(i, ld, b)] = vi;
+                if (A.a) A.a[at(i, ld, b)] = ai;
+            }
             if (i == 0) { vmin = vmaxs = vi; latmax = li; amax = amin = ai; }
             else {  // np.max / np.min
                 vmin = (vi < vmin) ? vi : vmin;
@@ -132,7 +155,7 @@ STO_HD void qss_finish(const QssArgs& A, int b, int status, int64_t steps, int i
             }
             bad = bad || !(vi == vi);
             if (i + 1 < N) {
-                const double vn = A.v[at(i + 1, ld, b)];
+                const double vn = S.v(i + 1);
                 const double t = A.df[at(i, ld, b)] / (0.5 * (vi + vn));
                 if (A.tseg) A.tseg[at(i + 1, ld, b)] = t;
                 lap = lap + t;
@@ -287,7 +310,7 @@ STO_HD void qss_plain_candidate(const QssArgs& A, const sto_vehicle_f64& V, int 
             if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
         }
     }
-    if (active) qss_finish(A, b, status, steps, iters);
+    if (active) qss_finish(A, StateSoA{A, b}, false, b, status, steps, iters);
 }
 
 }  // namespace sto

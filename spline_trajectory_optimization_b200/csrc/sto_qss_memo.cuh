@@ -166,13 +166,16 @@ STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double 
 // Evaluate the front step p -> q, apply it and record its memo.  Returns true when the front stops.
 STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64& V, int b, bool fwd, int p, int q,
                       double lat0, int& status, bool& spawn, bool& changed) {
-    const int ld = A.ld, N = A.N;
+    const int N = A.N;
     const int d = fwd ? 1 : 0;
-    // all six state words are fetched up front: one overlapped memory round trip per evaluation
-    const double vp = A.v[at(p, ld, b)], ap = A.a[at(p, ld, b)];
-    const double dd = A.dd[at(fwd ? p : q, ld, b)];
-    const double Rq = A.R[at(q, ld, b)], gq = gsb_at(A, q);
-    const double vq = A.v[at(q, ld, b)], aq_old = A.a[at(q, ld, b)];
+    // both 32-byte records are fetched up front (adjacent in memory): one overlapped round trip per evaluation
+    double* rec = A.rec + (size_t)b * N * 4;
+    double* rp = rec + 4 * (size_t)p;
+    double* rq = rec + 4 * (size_t)q;
+    const double vp = rp[0], ap = rp[1], ddp = rp[2];
+    const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
+    const double dd = fwd ? ddp : ddq;   // chord between p and q is stored at the lower sample
+    const double gq = gsb_at(A, q);
     spawn = false;
     changed = false;
 #if defined(STO_HOSTSIM_COUNTERS)
@@ -186,8 +189,8 @@ STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64&
         const double gg = g * g;
         const double aq = (fwd ? gg - vp2 : vp2 - gg) / (2 * dd);
         if (!same_bits(vq, g) || !same_bits(aq_old, aq)) {
-            A.v[at(q, ld, b)] = g;
-            A.a[at(q, ld, b)] = aq;
+            rq[0] = g;
+            rq[1] = aq;
             memo_invalidate(C, q, N);
             changed = true;
         }
@@ -198,8 +201,8 @@ STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64&
     if (fwd) { C.stop(1).set(p); C.cont(1).clear(p); return true; }
     const double vi = init_speed(lat0, Rq, gq, V.max_speed);
     if (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) {
-        A.v[at(q, ld, b)] = vi;
-        A.a[at(q, ld, b)] = 0.0;
+        rq[0] = vi;
+        rq[1] = 0.0;
         memo_invalidate(C, q, N);
         changed = true;
     }
@@ -411,9 +414,13 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #endif
     int status = 0;
     if (active) {
-        for (int i = 0; i < N; ++i) {  // simulator.py:133-147
-            A.v[at(i, ld, b)] = init_speed(lat0, A.R[at(i, ld, b)], gsb_at(A, i), V.max_speed);
-            A.a[at(i, ld, b)] = 0.0;
+        double* rec = A.rec + (size_t)b * N * 4;
+        for (int i = 0; i < N; ++i) {  // simulator.py:133-147; sample-major inputs -> this candidate's records
+            const double Ri = A.R[at(i, ld, b)];
+            rec[4 * (size_t)i + 0] = init_speed(lat0, Ri, gsb_at(A, i), V.max_speed);
+            rec[4 * (size_t)i + 1] = 0.0;
+            rec[4 * (size_t)i + 2] = A.dd[at(i, ld, b)];
+            rec[4 * (size_t)i + 3] = Ri;
         }
         for (int w = 0; w < W.W; ++w) {
             const int nb = N - 64 * w;
@@ -469,7 +476,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         STO_CLK(5)
     }
     STO_CLK(6)
-    if (active) qss_finish(A, b, status, steps, iters);
+    if (active) qss_finish(A, StateRec{A.rec + (size_t)b * N * 4}, true, b, status, steps, iters);
     STO_CLK(7)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];

@@ -75,6 +75,8 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
         std::vector<std::vector<char>> keep;
         sto::MemoWork W = sto::carve_memo([&](size_t n) { keep.emplace_back(n); return (void*)keep.back().data(); },
                                           N, (size_t)ld, cap);
+        std::vector<double> rec((size_t)N * ld * 4);
+        A.rec = rec.data();
         std::vector<unsigned long long> planes((size_t)6 * W.W + STO_LIST_RING);   // a "warp of one": stride 1, lane 0
         const sto::MemoCtx C = sto::memo_bind(planes.data(), 1, 0, N, W.W);
         for (int b = 0; b < B; ++b) sto::qss_memo_candidate(A, W, C, *V, b, true);
