@@ -181,9 +181,11 @@ STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64&
 #if defined(STO_HOSTSIM_COUNTERS)
     ++g_memo_evals[d];
 #endif
-    if (vp == 0.0) { status |= STO_CAND_ZERO_SPEED; return true; }
+    // (no early exit before the arithmetic: a branch here makes the compiler split the record fetch into two
+    //  dependent round trips; with vp == 0 the step below just produces inf/nan that is never stored)
     double g, vp2;
     const bool valid = front_step_rt(V, fwd, vp, ap, dd, Rq, gq, g, vp2);
+    if (vp == 0.0) { status |= STO_CAND_ZERO_SPEED; return true; }  // reference: FloatingPointError (:164-165)
     if (valid) {
         if (vq < g) { C.stop(d).set(p); C.cont(d).clear(p); return true; }
         const double gg = g * g;
