@@ -133,13 +133,24 @@ STO_HD MemoCtx memo_bind(u64* base, int stride, int lane, int N, int W) {
     return MemoCtx{base + lane, stride, N, W, ring};
 }
 
-// The stored state of sample j changed: forget every memo that read it.
+// Clears bits {a, a+1 (mod N)} of one plane: one read-modify-write when both fall into the same 64-bit word.
+STO_HD void clear_pair(const Ring& r, int a, int a1) {
+    if ((a >> 6) == (a1 >> 6)) {
+        r.m[(size_t)(a >> 6) * r.stride] &= ~((1ull << (a & 63)) | (1ull << (a1 & 63)));
+    } else {
+        r.clear(a);
+        r.clear(a1);
+    }
+}
+
+// The stored state of sample j changed: forget every memo that read it (edges j -> j-1 and j+1 -> j of the
+// backward planes, j -> j+1 and j-1 -> j of the forward planes).
 STO_HD void memo_invalidate(const MemoCtx& C, int j, int N) {
     const int jn = (j + 1 == N) ? 0 : j + 1, jp = (j == 0) ? N - 1 : j - 1;
-    C.cont(0).clear(j);  C.stop(0).clear(j);    // edge j -> j-1
-    C.cont(0).clear(jn); C.stop(0).clear(jn);   // edge j+1 -> j
-    C.cont(1).clear(j);  C.stop(1).clear(j);    // edge j -> j+1
-    C.cont(1).clear(jp); C.stop(1).clear(jp);   // edge j-1 -> j
+    clear_pair(C.cont(0), j, jn);
+    clear_pair(C.stop(0), j, jn);
+    clear_pair(C.cont(1), jp, j);
+    clear_pair(C.stop(1), jp, j);
 }
 
 // front_step<FWD> of sto_qss.cuh with the direction as a run-time value (lanes of one warp may be in different
@@ -316,8 +327,11 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
             if (stopped) { L &= ~bit; --nlive; }
             if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
-            // later rows of this word may now face a dirty edge: re-read the window after a state change
-            att = changed ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
+            // Forward: the next row reads the sample just written, so later rows of this word may now face a dirty
+            // edge -> re-read the window.  Backward: row i writes the sample row i-1 has already left; the one later
+            // row it can reach is the seam (row 0 writes what row N-1 reads), which lives in the last word, whose
+            // window is only formed when the walk gets there (N >= 128: never word 0).
+            att = (changed && FWD) ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
         }
         STO_SUBCLK(1)
     }
