@@ -240,6 +240,18 @@ int check_vehicle(const sto_vehicle_f64* v) {
     return STO_OK;
 }
 
+// Large-batch variant: bit planes in global memory (candidate-major, L1/L2 cached), only the 2 KB prefetch ring in
+// shared memory, so residency is bounded by registers (~19 warps/SM) instead of 2.2 KB of planes per candidate.
+__global__ void qss_memo_gplanes_kernel(sto::QssArgs A, sto::MemoWork W, int lanes,
+                                        const __grid_constant__ sto_vehicle_f64 V) {
+    __shared__ int32_t ring[STO_LIST_RING * 32];
+    bool active;
+    const int b = candidate_of_thread(lanes, A.B, active);
+    const int lane = threadIdx.x & 31;
+    const sto::MemoCtx C = sto::memo_bind_global(W.gplanes + (size_t)b * 6 * W.W, ring, 32, lane, A.N, W.W);
+    sto::qss_memo_candidate(A, W, C, V, b, active);
+}
+
 // Candidates per warp for the QSS kernels: aim for a few warps on each of the 148 SMs before filling warps.
 int pick_lanes(int B, size_t smem_per_candidate) {
     int lanes = 32;
@@ -264,6 +276,14 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
         else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
+        const char* pl = getenv("STO_QSS_PLANES");
+        if (pl && pl[0] == 'g') {   // experimental: planes in global memory
+            const int lanes = pick_lanes(A.B, 0);
+            const int warps = (A.B + lanes - 1) / lanes;
+            qss_memo_gplanes_kernel<<<warps, 32, 0, st>>>(A, w.memo, lanes, *vehicle);
+            STO_CUDA(cudaGetLastError());
+            return STO_OK;
+        }
         const size_t per_cand = sto::memo_smem_bytes(A.N);
         const int lanes = pick_lanes(A.B, per_cand);
         const int warps = (A.B + lanes - 1) / lanes;

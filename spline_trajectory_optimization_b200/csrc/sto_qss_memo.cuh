@@ -36,6 +36,7 @@ struct MemoWork {
                          // creation order: a front at sample p with offset s = (k-1) mod N behaves like original
                          // row (p + s) mod N (backward) / (p - s) mod N (forward)
     int W;               // 64-bit words per bit plane = ceil(N / 64)
+    unsigned long long* gplanes;  // [ld][6 * W] candidate-major bit planes in global memory (large-batch variant)
 };
 
 // Bytes of bit-plane storage per candidate (six planes: live B/F, cont B/F, stop B/F).  On the device the planes
@@ -49,6 +50,7 @@ inline MemoWork carve_memo(Alloc alloc, int N, size_t ld, int cap) {
     w.W = (N + 63) / 64;
     w.spB = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
     w.spF = (int32_t*)alloc((size_t)cap * ld * sizeof(int32_t));
+    w.gplanes = (unsigned long long*)alloc((size_t)6 * w.W * ld * sizeof(unsigned long long));
     return w;
 }
 
@@ -113,7 +115,8 @@ struct Ring {
 struct MemoCtx {
     u64* base;
     int stride, N, W;
-    int32_t* ring;  // shared-memory prefetch ring of this lane for the re-spawned lists: slot k at ring[k * stride]
+    int32_t* ring;  // shared-memory prefetch ring of this lane for the re-spawned lists: slot k at ring[k * ring_stride]
+    int ring_stride;
     STO_HD Ring plane(int k) const { return Ring{base + (size_t)k * W * stride, stride, N, W}; }
     STO_HD Ring live(int d) const { return plane(0 + d); }   // d = 0 backward (edge p -> p-1), 1 forward (p -> p+1)
     STO_HD Ring cont(int d) const { return plane(2 + d); }
@@ -127,10 +130,17 @@ struct MemoCtx {
 // Shared memory per candidate: six bit planes + the list prefetch ring.
 STO_HD size_t memo_smem_bytes(int N) { return memo_plane_bytes(N) + STO_LIST_RING * sizeof(int32_t); }
 
+// Planes in global memory (candidate-major, stride 1), prefetch ring in shared memory ([STO_LIST_RING][ring_stride]).
+STO_HD MemoCtx memo_bind_global(u64* planes, int32_t* ring, int ring_stride, int lane, int N, int W) {
+    MemoCtx C{planes, 1, N, W, ring + lane};
+    C.ring_stride = ring_stride;
+    return C;
+}
+
 // base: [6 planes][W words][stride lanes] u64, followed by [STO_LIST_RING][stride] int32.
 STO_HD MemoCtx memo_bind(u64* base, int stride, int lane, int N, int W) {
     int32_t* ring = reinterpret_cast<int32_t*>(base + (size_t)6 * W * stride) + lane;
-    return MemoCtx{base + lane, stride, N, W, ring};
+    return MemoCtx{base + lane, stride, N, W, ring, stride};
 }
 
 // Clears bits {a, a+1 (mod N)} of one plane: one read-modify-write when both fall into the same 64-bit word.
@@ -369,7 +379,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
 #pragma unroll 1
     for (int k = 0; k < STO_LIST_RING; ++k) {
         if (k < nlist)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)(k * C.stride)),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)(k * C.ring_stride)),
                          "l"(list + at(k, ld, b)) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -379,7 +389,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
         while (r < nlist) {
 #if defined(__CUDA_ARCH__)
             asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");
-            const int slot = (r & (STO_LIST_RING - 1)) * C.stride;
+            const int slot = (r & (STO_LIST_RING - 1)) * C.ring_stride;
             iv = C.ring[slot];
             if (r + STO_LIST_RING < nlist)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
