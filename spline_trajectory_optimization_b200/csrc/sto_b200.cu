@@ -276,8 +276,14 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
         else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
-        const char* pl = getenv("STO_QSS_PLANES");
-        if (pl && pl[0] == 'g') {   // experimental: planes in global memory
+        // Where the bit planes live: shared memory while the whole batch is resident in one wave (small batches are
+        // bound by the per-candidate dependent chain, and LDS beats an L1 hit), global memory (L1/L2 cached) beyond
+        // that, where throughput is bound by how many candidates an SM can keep in flight (measured on B200, Monza:
+        // 4,096 candidates 86 ms smem vs 92 ms global; 32,768 candidates 299 ms smem vs 186 ms global).
+        const char* pl = getenv("STO_QSS_PLANES");   // tuning override: "s" / "g"
+        const bool global_planes = pl ? (pl[0] == 'g')
+                                      : ((size_t)A.B * sto::memo_smem_bytes(A.N) > (size_t)148 * kMemoSmemBudget);
+        if (global_planes) {
             const int lanes = pick_lanes(A.B, 0);
             const int warps = (A.B + lanes - 1) / lanes;
             qss_memo_gplanes_kernel<<<warps, 32, 0, st>>>(A, w.memo, lanes, *vehicle);
