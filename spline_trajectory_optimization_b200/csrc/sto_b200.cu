@@ -80,7 +80,7 @@ struct QssWork {
 constexpr size_t kMemoSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use on sm_100a
 inline int effective_impl(int N, int impl) {
     // the memoised kernel keeps six bit planes per candidate in shared memory: 48 * ceil(N/64) bytes
-    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N && sto::memo_smem_bytes(N) <= kMemoSmemBudget)
+    return (impl == STO_QSS_MEMO && N >= STO_QSS_MEMO_MIN_N && sto::memo_smem_bytes(N, 1) <= kMemoSmemBudget)
                ? STO_QSS_MEMO : STO_QSS_PLAIN;
 }
 QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool need_state) {
@@ -155,15 +155,18 @@ __global__ void qss_plain_kernel(sto::QssArgs A, int lanes, const __grid_constan
     sto::qss_plain_candidate<OWNER>(A, V, b, active);
 }
 
-extern __shared__ unsigned long long sto_planes[];  // [6 planes][W words][lanes] per warp, one column per lane
+extern __shared__ unsigned long long sto_planes[];  // [6 planes][W words][cpw candidates], then the per-lane rings
 
-__global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int lanes, const __grid_constant__ sto_vehicle_f64 V) {
-    bool active;
-    const int b = candidate_of_thread(lanes, A.B, active);
-    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
-    unsigned long long* base = sto_planes + (size_t)warp_in_block * (sto::memo_smem_bytes(A.N) / 8) * lanes;
-    const sto::MemoCtx C = sto::memo_bind(base, lanes, lane < lanes ? lane : 0, A.N, W.W);
-    sto::qss_memo_candidate(A, W, C, V, b, active);
+// One warp per CTA hosting `cpw` candidates, each run by a group of G lanes (see sto_qss_memo.cuh, "lane groups").
+template <int G>
+__global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
+    const int lane = threadIdx.x & 31, warp = blockIdx.x;
+    const int grp = lane / G, g = lane % G;
+    const int b = warp * cpw + grp;
+    const bool active = grp < cpw && b < A.B;
+    int32_t* ring = reinterpret_cast<int32_t*>(sto_planes + (size_t)6 * W.W * cpw);
+    const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, ring, 32, lane, A.N, W.W);
+    sto::qss_memo_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G);
 }
 
 __global__ void zero_status_kernel(int32_t* s, int B) {
@@ -249,7 +252,7 @@ __global__ void qss_memo_gplanes_kernel(sto::QssArgs A, sto::MemoWork W, int lan
     const int b = candidate_of_thread(lanes, A.B, active);
     const int lane = threadIdx.x & 31;
     const sto::MemoCtx C = sto::memo_bind_global(W.gplanes + (size_t)b * 6 * W.W, ring, 32, lane, A.N, W.W);
-    sto::qss_memo_candidate(A, W, C, V, b, active);
+    sto::qss_memo_candidate<1>(A, W, C, V, b, active, 0, lane);
 }
 
 // Candidates per warp for the QSS kernels: aim for a few warps on each of the 148 SMs before filling warps.
@@ -282,7 +285,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         // 4,096 candidates 86 ms smem vs 92 ms global; 32,768 candidates 299 ms smem vs 186 ms global).
         const char* pl = getenv("STO_QSS_PLANES");   // tuning override: "s" / "g"
         const bool global_planes = pl ? (pl[0] == 'g')
-                                      : ((size_t)A.B * sto::memo_smem_bytes(A.N) > (size_t)148 * kMemoSmemBudget);
+                                      : ((size_t)A.B * sto::memo_plane_bytes(A.N) > (size_t)148 * kMemoSmemBudget);
         if (global_planes) {
             const int lanes = pick_lanes(A.B, 0);
             const int warps = (A.B + lanes - 1) / lanes;
@@ -290,12 +293,29 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
             STO_CUDA(cudaGetLastError());
             return STO_OK;
         }
-        const size_t per_cand = sto::memo_smem_bytes(A.N);
-        const int lanes = pick_lanes(A.B, per_cand);
-        const int warps = (A.B + lanes - 1) / lanes;
-        const size_t smem = per_cand * lanes;  // one warp per CTA
-        STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        qss_memo_kernel<<<warps, 32, smem, st>>>(A, w.memo, lanes, *vehicle);
+        // Small batch: bound by the per-candidate dependent chain -> spend idle lanes on it.  A group of G lanes per
+        // candidate evaluates the backward sub-pass G fronts at a time; cpw <= 32 / G candidates share a warp.
+        int G = 4;
+        if (const char* e = getenv("STO_QSS_GROUP")) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4 || v == 8) G = v;
+        }
+        const size_t per_cand = sto::memo_plane_bytes(A.N);
+        int cpw = pick_lanes(A.B, per_cand);
+        if (cpw > 32 / G) cpw = 32 / G;
+        while (cpw > 1 && sto::memo_smem_bytes(A.N, cpw) > kMemoSmemBudget) cpw >>= 1;
+        const int warps = (A.B + cpw - 1) / cpw;
+        const size_t smem = sto::memo_smem_bytes(A.N, cpw);
+#define STO_LAUNCH_MEMO(GG)                                                                                          \
+    do {                                                                                                             \
+        STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        qss_memo_kernel<GG><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
+    } while (0)
+        if (G == 8) STO_LAUNCH_MEMO(8);
+        else if (G == 4) STO_LAUNCH_MEMO(4);
+        else if (G == 2) STO_LAUNCH_MEMO(2);
+        else STO_LAUNCH_MEMO(1);
+#undef STO_LAUNCH_MEMO
     }
     STO_CUDA(cudaGetLastError());
     return STO_OK;

@@ -58,6 +58,7 @@ typedef unsigned long long u64;
 #if defined(STO_HOSTSIM_COUNTERS)
 static long long g_memo_evals[2] = {0, 0};   // host-side test instrumentation only
 static long long g_memo_words[2] = {0, 0};
+static long long g_att_hist[2][16] = {};
 static long long g_sp_visits[2] = {0, 0}, g_sp_distinct[2] = {0, 0}, g_sp_on_live_orig[2] = {0, 0};
 static long long g_sp_evals[2] = {0, 0}, g_sp_changed[2] = {0, 0}, g_sp_maxlist[2] = {0, 0};
 #endif
@@ -127,20 +128,20 @@ struct MemoCtx {
 #define STO_LIST_RING 16  // entries in flight ahead of the list cursor (power of two)
 #endif
 
-// Shared memory per candidate: six bit planes + the list prefetch ring.
-STO_HD size_t memo_smem_bytes(int N) { return memo_plane_bytes(N) + STO_LIST_RING * sizeof(int32_t); }
-
 // Planes in global memory (candidate-major, stride 1), prefetch ring in shared memory ([STO_LIST_RING][ring_stride]).
 STO_HD MemoCtx memo_bind_global(u64* planes, int32_t* ring, int ring_stride, int lane, int N, int W) {
-    MemoCtx C{planes, 1, N, W, ring + lane};
-    C.ring_stride = ring_stride;
-    return C;
+    return MemoCtx{planes, 1, N, W, ring + lane, ring_stride};
 }
 
-// base: [6 planes][W words][stride lanes] u64, followed by [STO_LIST_RING][stride] int32.
-STO_HD MemoCtx memo_bind(u64* base, int stride, int lane, int N, int W) {
-    int32_t* ring = reinterpret_cast<int32_t*>(base + (size_t)6 * W * stride) + lane;
-    return MemoCtx{base + lane, stride, N, W, ring, stride};
+// Planes in shared memory: [6 planes][W words][stride candidates] u64, this candidate in column `col`; the prefetch
+// ring ([STO_LIST_RING][ring_stride] int32) is per LANE (the lanes of a group walk the lists redundantly).
+STO_HD MemoCtx memo_bind(u64* planes, int stride, int col, int32_t* ring, int ring_stride, int lane, int N, int W) {
+    return MemoCtx{planes + col, stride, N, W, ring + lane, ring_stride};
+}
+
+// Shared memory of one warp hosting `cands` candidates.
+STO_HD size_t memo_smem_bytes(int N, int cands) {
+    return memo_plane_bytes(N) * (size_t)cands + (size_t)STO_LIST_RING * 32 * sizeof(int32_t);
 }
 
 // Clears bits {a, a+1 (mod N)} of one plane: one read-modify-write when both fall into the same 64-bit word.
@@ -184,64 +185,97 @@ STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double 
     return smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
 }
 
-// Evaluate the front step p -> q, apply it and record its memo.  Returns true when the front stops.
-STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64& V, int b, bool fwd, int p, int q,
-                      double lat0, int& status, bool& spawn, bool& changed) {
+// Outcome of one front step, computed without side effects (eval_pure) and committed separately (apply_res), so
+// that several mutually independent steps can be evaluated at once and committed in row order.
+enum { EV_NONE = 0, EV_KILL, EV_STOP, EV_WRITE, EV_KEEP, EV_SPAWN, EV_RESPAWN, EV_ZERO };
+struct EvalRes {
+    int kind;        // EV_KILL  front on a STOP-memo edge: stops, nothing evaluated
+                     // EV_STOP  evaluated: a slower speed is stored at q (or forward step infeasible) -> stop, memo STOP
+                     // EV_WRITE valid, (v, a) of q change; EV_KEEP valid, q already holds exactly these values
+                     // EV_SPAWN infeasible backward step, q is re-initialised (changes); EV_RESPAWN same, q unchanged
+                     // EV_ZERO  v_p == 0: the reference raises (simulator.py:164-165)
+    double v_new, a_new;
+};
+
+STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool fwd, int p, int q, double lat0) {
     const int N = A.N;
-    const int d = fwd ? 1 : 0;
     // both 32-byte records are fetched up front (adjacent in memory): one overlapped round trip per evaluation
-    double* rec = A.rec + (size_t)b * N * 4;
-    double* rp = rec + 4 * (size_t)p;
-    double* rq = rec + 4 * (size_t)q;
+    const double* rec = A.rec + (size_t)b * N * 4;
+    const double* rp = rec + 4 * (size_t)p;
+    const double* rq = rec + 4 * (size_t)q;
     const double vp = rp[0], ap = rp[1], ddp = rp[2];
     const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
     const double dd = fwd ? ddp : ddq;   // chord between p and q is stored at the lower sample
     const double gq = gsb_at(A, q);
-    spawn = false;
-    changed = false;
 #if defined(STO_HOSTSIM_COUNTERS)
-    ++g_memo_evals[d];
+    ++g_memo_evals[fwd ? 1 : 0];
 #endif
     // (no early exit before the arithmetic: a branch here makes the compiler split the record fetch into two
     //  dependent round trips; with vp == 0 the step below just produces inf/nan that is never stored)
     double g, vp2;
     const bool valid = front_step_rt(V, fwd, vp, ap, dd, Rq, gq, g, vp2);
-    if (vp == 0.0) { status |= STO_CAND_ZERO_SPEED; return true; }  // reference: FloatingPointError (:164-165)
+    EvalRes r;
+    r.v_new = 0.0; r.a_new = 0.0;
+    if (vp == 0.0) { r.kind = EV_ZERO; return r; }
     if (valid) {
-        if (vq < g) { C.stop(d).set(p); C.cont(d).clear(p); return true; }
+        if (vq < g) { r.kind = EV_STOP; return r; }
         const double gg = g * g;
         const double aq = (fwd ? gg - vp2 : vp2 - gg) / (2 * dd);
-        if (!same_bits(vq, g) || !same_bits(aq_old, aq)) {
-            rq[0] = g;
-            rq[1] = aq;
+        r.v_new = g; r.a_new = aq;
+        r.kind = (!same_bits(vq, g) || !same_bits(aq_old, aq)) ? EV_WRITE : EV_KEEP;
+        return r;
+    }
+    if (fwd) { r.kind = EV_STOP; return r; }
+    const double vi = init_speed(lat0, Rq, gq, V.max_speed);
+    r.v_new = vi;
+    r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;
+    return r;
+}
+
+// Commits an outcome: state write, memo invalidation, the edge's own memo.  Returns true when the front stops.
+STO_HD bool apply_res(const QssArgs& A, const MemoCtx& C, int b, bool fwd, int p, int q, const EvalRes& r,
+                      int& status, bool& spawn, bool& changed) {
+    const int N = A.N, d = fwd ? 1 : 0;
+    spawn = false;
+    changed = false;
+    switch (r.kind) {
+        case EV_KILL: return true;
+        case EV_ZERO: status |= STO_CAND_ZERO_SPEED; return true;
+        case EV_STOP: C.stop(d).set(p); C.cont(d).clear(p); return true;
+        case EV_WRITE: case EV_SPAWN: {
+            double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
+            rq[0] = r.v_new;
+            rq[1] = r.a_new;
             memo_invalidate(C, q, N);
             changed = true;
+            break;
         }
+        default: break;
+    }
+    if (r.kind == EV_WRITE || r.kind == EV_KEEP) {
         C.cont(d).set(p);  // re-running this step on the state as it now stands rewrites the same values
         C.stop(d).clear(p);
         return false;
     }
-    if (fwd) { C.stop(1).set(p); C.cont(1).clear(p); return true; }
-    const double vi = init_speed(lat0, Rq, gq, V.max_speed);
-    if (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) {
-        rq[0] = vi;
-        rq[1] = 0.0;
-        memo_invalidate(C, q, N);
-        changed = true;
-    }
-    spawn = true;
+    spawn = true;  // EV_SPAWN / EV_RESPAWN: never memoised
     return true;
+}
+
+// Evaluate the front step p -> q, apply it and record its memo.  Returns true when the front stops.
+STO_HD bool memo_step(const QssArgs& A, const MemoCtx& C, const sto_vehicle_f64& V, int b, bool fwd, int p, int q,
+                      double lat0, int& status, bool& spawn, bool& changed) {
+    const EvalRes r = eval_pure(A, V, b, fwd, p, q, lat0);
+    return apply_res(A, C, b, fwd, p, q, r, status, spawn, changed);
 }
 
 // A new row at sample q (simulator.py:238-254).  It first acts in the next outer iteration (offset s+1), so its
 // virtual backward row is (q + s + 1) mod N; it is parked behind the live backward list ([nB, nB + nnew)) and
 // folded into both lists at the end of the iteration.
-STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s, int nB, int& nnew, int& status) {
+STO_HD void memo_spawn(const QssArgs& A, const MemoWork& W, int b, int q, int s, int nB, int nnew, int& status) {
     if (nB + nnew >= A.cap) { status |= STO_CAND_ROW_OVERFLOW; return; }
     int iv = q + s + 1;
     if (iv >= A.N) iv -= A.N;
     W.spB[at(nB + nnew, A.ld, b)] = iv;
-    ++nnew;
 }
 
 
@@ -307,6 +341,9 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                     if (start >= N) start -= N;
                     if (start < 0) start += N;
                     att = L & ~cont.window(start);              // fronts that are not on a known-clean edge
+#if defined(STO_HOSTSIM_COUNTERS)
+                    if (att) { int c = popc64(att); ++g_att_hist[d][c > 15 ? 15 : c]; }
+#endif
                     donemask = 0;
                     open = true;
                 }
@@ -336,7 +373,7 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             bool changed = false, spawn = false;
             const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
             if (stopped) { L &= ~bit; --nlive; }
-            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            if (spawn) { memo_spawn(A, W, b, q, s, nB, nnew, status); ++nnew; }
             // Forward: the next row reads the sample just written, so later rows of this word may now face a dirty
             // edge -> re-read the window.  Backward: row i writes the sample row i-1 has already left; the one later
             // row it can reach is the seam (row 0 writes what row N-1 reads), which lives in the last word, whose
@@ -344,6 +381,119 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             att = (changed && FWD) ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
         }
         STO_SUBCLK(1)
+    }
+}
+
+// ---- lane groups -------------------------------------------------------------------------------------------------
+// A candidate may be run by a GROUP of G lanes.  All lanes of a group carry the same registers and execute the same
+// control flow (redundantly, for free in SIMT) EXCEPT in the backward sub-pass over the original rows, which is a
+// Jacobi step: row i reads samples (p, p-1) and writes p-1, and no later row of the sub-pass reads what it writes
+// (bar the seam, which sits in another word).  So up to G consecutive dirty fronts of a word are evaluated at once,
+// one per lane, against the state as it stood, and committed in row order - bit-identical to doing them one by one,
+// G times shorter on the critical path.  (Dirty backward fronts cluster: half of them sit in words with >= 15.)
+STO_HD int kth_bit(u64 x, int k) {
+    for (int i = 0; i < k; ++i) x &= x - 1ull;
+    return ctz64(x);
+}
+STO_HD u64 lowest_bits(u64 x, int k) {
+    u64 m = 0;
+    for (int i = 0; i < k; ++i) { const u64 low = x & (~x + 1ull); m |= low; x ^= low; }
+    return m;
+}
+
+template <int G>
+STO_HD void memo_bwd_rows_group(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                                int b, bool skip, int s, double lat0, int nB, int& nnew, int& nlive, u64& words,
+                                int64_t& steps, int& status, int g, int lane0) {
+    const int N = A.N, NW = W.W;
+    const Ring live = C.live(0), cont = C.cont(0), stop = C.stop(0);
+    const bool use_mask = NW <= 64;
+    u64 todo = use_mask ? words : 0ull, L = 0, att = 0;
+    int w = 0, start = 0;
+    bool open = false;
+    (void)g; (void)lane0;
+    for (;;) {
+        bool pending = false;
+        if (!skip) {
+            for (;;) {  // identical on every lane of the group
+                if (!open) {
+                    if (use_mask) {
+                        if (!todo) break;
+                        w = ctz64(todo);
+                        todo &= todo - 1ull;
+                    } else if (w >= NW) break;
+                    L = live.word(w);
+                    if (!L) { if (use_mask) words &= ~(1ull << w); else ++w; continue; }
+                    steps += popc64(L);
+                    start = 64 * w - s;
+                    if (start < 0) start += N;
+                    att = L & ~cont.window(start);
+                    open = true;
+                }
+                if (!att) {
+                    live.set_word(w, L);
+                    if (use_mask) { if (!L) words &= ~(1ull << w); } else ++w;
+                    open = false;
+                    continue;
+                }
+                pending = true;
+                break;
+            }
+        }
+        if (!warp_any(pending)) break;
+        const int n = pending ? ((popc64(att) < G) ? popc64(att) : G) : 0;
+#if defined(__CUDA_ARCH__)
+        // evaluate: lane g takes the g-th dirty front of the word
+        EvalRes res;
+        res.kind = EV_NONE; res.v_new = 0.0; res.a_new = 0.0;
+        int p = 0, q = 0;
+        if (g < n) {
+            p = 64 * w + kth_bit(att, g) - s;
+            if (p < 0) p += N;
+            q = (p == 0) ? N - 1 : p - 1;
+            if (stop.test(p)) res.kind = EV_KILL;
+            else res = eval_pure(A, V, b, false, p, q, lat0);
+        }
+        __syncwarp();
+        // commit in row order; every lane of the group mirrors the bookkeeping
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            int flags = 0;
+            if (g == k && res.kind != EV_NONE) {
+                bool spawn, changed;
+                int st = 0;
+                const bool stopped = apply_res(A, C, b, false, p, q, res, st, spawn, changed);
+                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, st);
+                flags = (stopped ? 1 : 0) | (spawn ? 2 : 0) | (st << 2);
+            }
+            __syncwarp();
+            flags = __shfl_sync(0xffffffffu, flags, lane0 + k);
+            if (k < n) {
+                if (flags & 1) { L &= ~(1ull << kth_bit(att, k)); --nlive; }
+                if (flags & 2) ++nnew;
+                status |= flags >> 2;
+            }
+        }
+#else
+        // host emulation of the G lanes: all evaluations first (frozen state), then the commits in row order
+        EvalRes res[G];
+        int pp[G], qq[G];
+        for (int k = 0; k < n; ++k) {
+            int p = 64 * w + kth_bit(att, k) - s;
+            if (p < 0) p += N;
+            pp[k] = p;
+            qq[k] = (p == 0) ? N - 1 : p - 1;
+            if (stop.test(p)) { res[k].kind = EV_KILL; res[k].v_new = res[k].a_new = 0.0; }
+            else res[k] = eval_pure(A, V, b, false, p, qq[k], lat0);
+        }
+        for (int k = 0; k < n; ++k) {
+            bool spawn, changed;
+            const bool stopped = apply_res(A, C, b, false, pp[k], qq[k], res[k], status, spawn, changed);
+            if (spawn) { memo_spawn(A, W, b, qq[k], s, nB, nnew, status); ++nnew; }
+            if (stopped) { L &= ~(1ull << kth_bit(att, k)); --nlive; }
+        }
+#endif
+        att &= ~lowest_bits(att, n);
     }
 }
 
@@ -419,7 +569,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
 #if defined(STO_HOSTSIM_COUNTERS)
             ++g_sp_evals[d]; if (changed) ++g_sp_changed[d];
 #endif
-            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, status);
+            if (spawn) { memo_spawn(A, W, b, q, s, nB, nnew, status); ++nnew; }
             if (!stopped) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; }
         }
         STO_SUBCLK(3)
@@ -428,8 +578,9 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
 }
 
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
+template <int G>
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
-                               bool active) {
+                               bool active, int g, int lane0) {
     const int N = A.N, ld = A.ld;
     const double lat0 = max_lat_acc(V, 0.0);
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
@@ -440,15 +591,20 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #endif
     int status = 0;
     if (active) {
+#if defined(__CUDA_ARCH__)
+        const int GS = G;   // the group's lanes fill interleaved slices
+#else
+        const int GS = 1;   // host emulation: one caller plays every lane of the group
+#endif
         double* rec = A.rec + (size_t)b * N * 4;
-        for (int i = 0; i < N; ++i) {  // simulator.py:133-147; sample-major inputs -> this candidate's records
+        for (int i = g; i < N; i += GS) {  // simulator.py:133-147; sample-major inputs -> this candidate's records
             const double Ri = A.R[at(i, ld, b)];
             rec[4 * (size_t)i + 0] = init_speed(lat0, Ri, gsb_at(A, i), V.max_speed);
             rec[4 * (size_t)i + 1] = 0.0;
             rec[4 * (size_t)i + 2] = A.dd[at(i, ld, b)];
             rec[4 * (size_t)i + 3] = Ri;
         }
-        for (int w = 0; w < W.W; ++w) {
+        for (int w = g; w < W.W; w += GS) {
             const int nb = N - 64 * w;
             const u64 ones = (nb >= 64) ? ~0ull : ((1ull << nb) - 1ull);
             for (int d = 0; d < 2; ++d) {
@@ -458,6 +614,9 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             }
         }
     }
+#if defined(__CUDA_ARCH__)
+    if (G > 1) __syncwarp();  // the group's lanes filled disjoint slices of the records and planes
+#endif
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
     u64 wordsB = (W.W >= 64) ? ~0ull : ((1ull << W.W) - 1ull), wordsF = wordsB;  // words with running fronts
     int nB = 0, nF = 0;  // live re-spawned fronts per direction
@@ -468,7 +627,11 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
-        memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
+        if (G > 1)
+            memo_bwd_rows_group<G>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status,
+                                   g, lane0);
+        else
+            memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
         STO_CLK(1)
         const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
@@ -502,7 +665,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         STO_CLK(5)
     }
     STO_CLK(6)
-    if (active) qss_finish(A, StateRec{A.rec + (size_t)b * N * 4}, true, b, status, steps, iters);
+    if (active && g == 0) qss_finish(A, StateRec{A.rec + (size_t)b * N * 4}, true, b, status, steps, iters);
     STO_CLK(7)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];

@@ -78,8 +78,17 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
         std::vector<double> rec((size_t)N * ld * 4);
         A.rec = rec.data();
         std::vector<unsigned long long> planes((size_t)6 * W.W + STO_LIST_RING);   // a "warp of one": stride 1, lane 0
-        const sto::MemoCtx C = sto::memo_bind(planes.data(), 1, 0, N, W.W);
-        for (int b = 0; b < B; ++b) sto::qss_memo_candidate(A, W, C, *V, b, true);
+        std::vector<int32_t> ring(STO_LIST_RING);
+        const sto::MemoCtx C = sto::memo_bind(planes.data(), 1, 0, ring.data(), 1, 0, N, W.W);
+        // impl 1: one lane per candidate; impl 100 + G: emulated groups of G lanes (backward rows G at a time)
+        for (int b = 0; b < B; ++b) {
+            switch (impl) {
+                case 102: sto::qss_memo_candidate<2>(A, W, C, *V, b, true, 0, 0); break;
+                case 104: sto::qss_memo_candidate<4>(A, W, C, *V, b, true, 0, 0); break;
+                case 108: sto::qss_memo_candidate<8>(A, W, C, *V, b, true, 0, 0); break;
+                default: sto::qss_memo_candidate<1>(A, W, C, *V, b, true, 0, 0); break;
+            }
+        }
     }
     return 0;
 }
@@ -88,6 +97,10 @@ void hostsim_sp_counters(long long* out12, int reset) {
     long long* src[6] = {sto::g_sp_visits, sto::g_sp_distinct, sto::g_sp_on_live_orig, sto::g_sp_evals, sto::g_sp_changed,
                          sto::g_sp_maxlist};
     for (int k = 0; k < 6; ++k) { out12[2 * k] = src[k][0]; out12[2 * k + 1] = src[k][1]; if (reset) src[k][0] = src[k][1] = 0; }
+}
+
+void hostsim_att_hist(long long* out32) {
+    for (int d = 0; d < 2; ++d) for (int k = 0; k < 16; ++k) { out32[d * 16 + k] = sto::g_att_hist[d][k]; sto::g_att_hist[d][k] = 0; }
 }
 
 void hostsim_counters(long long* out4, int reset) {

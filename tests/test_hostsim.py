@@ -64,3 +64,20 @@ def test_generic_spline_eval_k5():
     x, y, yaw, rad = H.eval_spline(d["spl_t"], d["spl_cx"], d["spl_cy"], 5, d["ts"])
     assert np.array_equal(x, d["in_X"]) and np.array_equal(y, d["in_Y"])
     assert np.max(np.abs(rad - d["in_CURVATURE"]) / d["in_CURVATURE"]) < 1e-15
+
+
+@pytest.mark.parametrize("group", [2, 4, 8])
+@pytest.mark.parametrize("name", ["sim_s10k3_i2", "sim_s30k5_i3", "sim_oval_bank12"])
+def test_qss_lane_group_emulation_bit_exact(name, group):
+    """Lane groups: the backward sub-pass evaluates up to G consecutive dirty fronts of a word against the state as it
+    stood and commits them in row order (memo_bwd_rows_group).  Host emulation of the G lanes must reproduce the
+    one-at-a-time schedule bit for bit, including the front-step count."""
+    d = golden(name)
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    sb = np.sin(d["in_BANK"])
+    o = O.qss(d["in_X"], d["in_Y"], d["in_CURVATURE"], sb, ov, 0)
+    r = H.qss(100 + group, d["in_X"][None], d["in_Y"][None], d["in_CURVATURE"][None], sb, hv)
+    assert r["status"][0] == 0
+    for k in ("v", "a", "lat", "time"):
+        assert np.array_equal(r[k][0], o[k]), k
+    assert r["lap"][0] == o["lap"] and r["summary"][0, 6] == o["steps"]

@@ -14,10 +14,10 @@ from spline_trajectory_optimization_b200.evaluator import BatchedLineEvaluator  
 
 lib = _lib.load()
 rt, veh = bench.build_track(), bench.test_vehicle()
-configs = [tuple(int(x) for x in a.split(":")[:2]) + (a.split(":")[2] if a.count(":") > 1 else "s",) for a in sys.argv[1:]] or [(4096, 32, 's'), (4096, 8, 's')]
+configs = [tuple(int(x) for x in a.split(":")[:2]) + (a.split(":")[2] if a.count(":") > 1 else "s", a.split(":")[3] if a.count(":") > 2 else "4") for a in sys.argv[1:]] or [(4096, 8, 's', '4')]
 cache = {}
 ref = None
-for B, lanes, planes in configs:
+for B, lanes, planes, group in configs:
     if B not in cache:
         ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), veh, impl="memo")
         off = bench.make_offsets(rt, min(B, 4096), 1234)
@@ -27,6 +27,7 @@ for B, lanes, planes in configs:
     ev, d_off = cache[B]
     os.environ["STO_QSS_LANES"] = str(lanes)
     os.environ["STO_QSS_PLANES"] = planes
+    os.environ["STO_QSS_GROUP"] = group
     lib.sto_set_stage_timing(1)
     best = None
     for it in range(3):
@@ -40,6 +41,6 @@ for B, lanes, planes in configs:
     if ref is None:
         ref = lap[:4096].copy()
     same = np.array_equal(lap[:min(B, 4096)], ref[:min(B, 4096)])
-    print(f"B={B:7d} lanes={lanes:2d} planes={planes}  fit {best[1]:8.2f} ms  sample {best[2]:8.2f} ms  qss {best[3]:9.2f} ms  "
+    print(f"B={B:7d} lanes={lanes:2d} planes={planes} group={group}  fit {best[1]:8.2f} ms  sample {best[2]:8.2f} ms  qss {best[3]:9.2f} ms  "
           f"-> {B / (sum(best) * 1e-3):10.0f} cand/s   laps identical to first config: {same}  status ok: {not st.any().item()}",
           flush=True)
