@@ -268,6 +268,28 @@ def run_gpu_arm(args):
     ok = bool((st[:B] == 0).all().item())
     lap_host = lap[:B].cpu().numpy()
 
+    # ---- informational: throughput at the per-GPU batch of BASELINE configs[2] (262,144 candidates / 8 GPUs)
+    large = None
+    if args.large_batch and rank == 0 and world == 1:
+        BL = args.large_batch
+        off_l = torch.from_numpy(np.tile(host_off[0], ((BL + B - 1) // B, 1))[:BL]).to(dev)
+        d_l = ev.to_sample_major(off_l)
+        del off_l
+        ev.lap_times(d_l, B=BL)
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(2):
+            l_l, s_l = ev.lap_times(d_l, B=BL)
+        t1e.record()
+        torch.cuda.synchronize()
+        large = {"candidates_per_step": BL, "value": 2 * BL / (t0e.elapsed_time(t1e) * 1e-3), "unit": UNIT,
+                 "ms_per_step": t0e.elapsed_time(t1e) / 2, "all_status_ok": bool((s_l == 0).all().item()),
+                 "laps_equal_small_batch": bool(torch.equal(l_l[:B].cpu(), torch.from_numpy(
+                     ev.lap_times(d_off[0], B=B)[0].cpu().numpy()))),
+                 "note": "same candidates tiled; bit planes move to global memory at this size (DESIGN.md section 2)"}
+        del d_l
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -293,6 +315,8 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "lap_min_s": float(np.min(lap_host)), "lap_centre_line_s": float(lap_host[0]), "all_status_ok": ok,
         }
+        if large is not None:
+            line["large_batch"] = large
         if not args.no_cpu_baseline and world == 1:
             cb, olap = cpu_baseline_leg(rt, veh, host_off[(args.steps - 1) & 1])
             line["cpu_baseline"] = cb
@@ -312,6 +336,8 @@ def main():
     ap.add_argument("--qss", default="memo", choices=["memo", "plain"])
     ap.add_argument("--candidates", type=int, default=CANDIDATES_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-batch", type=int, default=32768,
+                    help="also report device-resident throughput at this batch size (0 = skip; N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
