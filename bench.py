@@ -235,6 +235,9 @@ def run_gpu_arm(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = B * world * args.steps / (ms_total * 1e-3)
+    # the clock sampler covers the device-timed region only: nvidia-smi polling takes the driver lock and would
+    # otherwise stretch every synchronous host call of the e2e leg below
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through the C ABI (H2D of the offsets + transpose + D2H of laps inside the call)
     for j in range(min(args.warmup, 2)):
@@ -249,7 +252,6 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / float(e2e_s.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline leg: per-kernel durations from CUDA events recorded on the launching stream inside the library
     lib.sto_set_stage_timing(1)
