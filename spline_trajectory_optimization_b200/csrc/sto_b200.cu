@@ -42,6 +42,12 @@ int pick_block(int B) {
     return 128;
 }
 inline int grid_for(int B, int block) { return (B + block - 1) / block; }
+// Lanes per candidate for kernels whose samples are independent: fill ~8 warps per SM before going one-per-candidate.
+int pick_split(int B, int N) {
+    int split = 1;
+    while (split < 32 && (long long)B * split < 148LL * 8 * 32 && N / (split * 2) >= 64) split <<= 1;
+    return split;
+}
 
 // ---- workspace carving ---------------------------------------------------------------------------------
 struct Carver {
@@ -114,9 +120,15 @@ __global__ void fit_kernel(sto::FitArgs A) {
     if (b < A.B) sto::fit_candidate(A, b);
 }
 
-__global__ void eval_kernel(sto::EvalArgs A) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < A.B) sto::eval_candidate(A, b);
+// `split` lanes share a candidate, each taking a contiguous slice of its samples (samples are independent): small
+// batches get split x more threads, which is what a latency-bound kernel needs.
+__global__ void eval_kernel(sto::EvalArgs A, int split) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = t / split, g = t % split;
+    if (b >= A.B) return;
+    const int per = (A.N + split - 1) / split;
+    const int j0 = g * per, j1 = (j0 + per < A.N) ? j0 + per : A.N;
+    sto::eval_range(A, b, j0, j1);
 }
 
 __global__ void eval_spline_kernel(sto::SplineEvalArgs A) {
@@ -382,8 +394,9 @@ int sto_sample_f64(const double* u, const double* cx, const double* cy, int M, c
     if (M < 3 || N < 1 || B < 1 || ld < B) return fail(STO_ERR_INVALID, "bad sizes");
     if (!u || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "u, cx, cy, ts must be non-NULL");
     sto::EvalArgs A{u, cx, cy, ts, M, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
-    const int block = pick_block(B);
-    eval_kernel<<<grid_for(B, block), block, 0, static_cast<cudaStream_t>(stream)>>>(A);
+    const int split = pick_split(B, N);
+    const int block = pick_block(B * split);
+    eval_kernel<<<grid_for(B * split, block), block, 0, static_cast<cudaStream_t>(stream)>>>(A, split);
     STO_CUDA(cudaGetLastError());
     return STO_OK;
 }
@@ -495,7 +508,11 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     stage_mark(2, st);
     // lap-only: x, y, yaw are never materialised; the chords and the radius are all the QSS reads
     sto::EvalArgs E{w.u, w.cx, w.cy, ts, M, N, B, ld, nullptr, nullptr, nullptr, w.R, w.qss.dd, w.qss.df};
-    eval_kernel<<<grid, block, 0, st>>>(E);
+    {
+        const int split = pick_split(B, N);
+        const int eblock = pick_block(B * split);
+        eval_kernel<<<grid_for(B * split, eblock), eblock, 0, st>>>(E, split);
+    }
     STO_CUDA(cudaGetLastError());
     stage_mark(3, st);
     sto::QssArgs A{};

@@ -116,55 +116,84 @@ STO_HD double turn_radius(double dx, double dy, double ddx, double ddy) {
     return 1.0 / fabs(curv);
 }
 
-STO_HD void eval_candidate(const EvalArgs& A, int b) {
-    const int M = A.M, N = A.N, ld = A.ld;
-    int i = 0;  // knot interval: U(i) <= x < U(i+1), clamped to [0, M-1]  (ell = i + 3)
-    int loaded = -1000;
+// Register window of one lane over its candidate's spline: knots tk[0..5] = U(i-2..i+3), coefficients c[i..i+3].
+struct EvalCursor {
+    int i, loaded;
     double tk[6], ccx[4], ccy[4];
-    double x_first = 0.0, y_first = 0.0, x_prev = 0.0, y_prev = 0.0;
-    const bool want_chord = A.chord_qss || A.chord_norm;
-    for (int j = 0; j < N; ++j) {
-        const double x = A.ts[j];
-        // scipy _find_interval, started from the previous interval
-        while (i > 0 && x < ((loaded == i) ? tk[2] : eval_knot(A, i, b))) { --i; }
-        while (i < M - 1 && x >= ((loaded == i) ? tk[3] : eval_knot(A, i + 1, b))) {
-            ++i;
-            if (loaded == i - 1) {  // slide the register window by one knot
-                tk[0] = tk[1]; tk[1] = tk[2]; tk[2] = tk[3]; tk[3] = tk[4]; tk[4] = tk[5];
-                tk[5] = eval_knot(A, i + 3, b);
-                ccx[0] = ccx[1]; ccx[1] = ccx[2]; ccx[2] = ccx[3]; ccx[3] = A.cx[at(i + 3, ld, b)];
-                ccy[0] = ccy[1]; ccy[1] = ccy[2]; ccy[2] = ccy[3]; ccy[3] = A.cy[at(i + 3, ld, b)];
-                loaded = i;
-            }
-        }
-        if (loaded != i) {
-            for (int n = 0; n < 6; ++n) tk[n] = eval_knot(A, i - 2 + n, b);
-            for (int n = 0; n < 4; ++n) { ccx[n] = A.cx[at(i + n, ld, b)]; ccy[n] = A.cy[at(i + n, ld, b)]; }
-            loaded = i;
-        }
-        double h0[4], h1[4], h2[4];
-        cubic_basis_d012(tk, x, h0, h1, h2);
-        const double px = dot4(ccx, h0), py = dot4(ccy, h0);
-        const double dx = dot4(ccx, h1), dy = dot4(ccy, h1);
-        const double ddx = dot4(ccx, h2), ddy = dot4(ccy, h2);
-        if (A.x) A.x[at(j, ld, b)] = px;
-        if (A.y) A.y[at(j, ld, b)] = py;
-        if (A.yaw) A.yaw[at(j, ld, b)] = atan2(dy, dx);
-        if (A.radius) A.radius[at(j, ld, b)] = turn_radius(dx, dy, ddx, ddy);
-        if (want_chord) {
-            if (j == 0) { x_first = px; y_first = py; }
-            else {
-                if (A.chord_qss) A.chord_qss[at(j - 1, ld, b)] = chord_qss(x_prev, y_prev, px, py);
-                if (A.chord_norm) A.chord_norm[at(j - 1, ld, b)] = chord_norm(x_prev, y_prev, px, py);
-            }
-            x_prev = px; y_prev = py;
+};
+
+// Position and first two derivatives at parameter x (scipy _find_interval walk from the previous interval).
+STO_HD void eval_at(const EvalArgs& A, int b, EvalCursor& c, double x, double* pos, double* d1, double* d2) {
+    const int M = A.M, ld = A.ld;
+    int i = c.i;
+    while (i > 0 && x < ((c.loaded == i) ? c.tk[2] : eval_knot(A, i, b))) { --i; }
+    while (i < M - 1 && x >= ((c.loaded == i) ? c.tk[3] : eval_knot(A, i + 1, b))) {
+        ++i;
+        if (c.loaded == i - 1) {  // slide the register window by one knot
+            c.tk[0] = c.tk[1]; c.tk[1] = c.tk[2]; c.tk[2] = c.tk[3]; c.tk[3] = c.tk[4]; c.tk[4] = c.tk[5];
+            c.tk[5] = eval_knot(A, i + 3, b);
+            c.ccx[0] = c.ccx[1]; c.ccx[1] = c.ccx[2]; c.ccx[2] = c.ccx[3]; c.ccx[3] = A.cx[at(i + 3, ld, b)];
+            c.ccy[0] = c.ccy[1]; c.ccy[1] = c.ccy[2]; c.ccy[2] = c.ccy[3]; c.ccy[3] = A.cy[at(i + 3, ld, b)];
+            c.loaded = i;
         }
     }
-    if (want_chord && N > 0) {
-        if (A.chord_qss) A.chord_qss[at(N - 1, ld, b)] = chord_qss(x_prev, y_prev, x_first, y_first);
-        if (A.chord_norm) A.chord_norm[at(N - 1, ld, b)] = chord_norm(x_prev, y_prev, x_first, y_first);
+    if (c.loaded != i) {
+        for (int n = 0; n < 6; ++n) c.tk[n] = eval_knot(A, i - 2 + n, b);
+        for (int n = 0; n < 4; ++n) { c.ccx[n] = A.cx[at(i + n, ld, b)]; c.ccy[n] = A.cy[at(i + n, ld, b)]; }
+        c.loaded = i;
+    }
+    c.i = i;
+    double h0[4], h1[4], h2[4];
+    cubic_basis_d012(c.tk, x, h0, h1, h2);
+    pos[0] = dot4(c.ccx, h0); pos[1] = dot4(c.ccy, h0);
+    d1[0] = dot4(c.ccx, h1);  d1[1] = dot4(c.ccy, h1);
+    d2[0] = dot4(c.ccx, h2);  d2[1] = dot4(c.ccy, h2);
+}
+
+// Samples j0 <= j < j1 of candidate b.  Samples are independent, so a candidate's range may be split over the
+// lanes of a group (each lane re-evaluates the one neighbour position its first / last chord needs).
+STO_HD void eval_range(const EvalArgs& A, int b, int j0, int j1) {
+    const int M = A.M, N = A.N, ld = A.ld;
+    if (j0 >= j1) return;
+    const bool want_chord = A.chord_qss || A.chord_norm;
+    EvalCursor c;
+    c.loaded = -1000;
+    double pos[2], d1[2], d2[2];
+    double x_prev = 0.0, y_prev = 0.0;
+    {   // start the interval walk near the right knot: candidates have u_i ~ i / M
+        double guess = A.ts[j0 > 0 ? j0 - 1 : 0] * (double)M;
+        int i = (guess > 0.0) ? (int)guess : 0;
+        c.i = (i > M - 1) ? M - 1 : i;
+    }
+    if (want_chord && j0 > 0) {
+        eval_at(A, b, c, A.ts[j0 - 1], pos, d1, d2);
+        x_prev = pos[0]; y_prev = pos[1];
+    }
+    for (int j = j0; j < j1; ++j) {
+        eval_at(A, b, c, A.ts[j], pos, d1, d2);
+        if (A.x) A.x[at(j, ld, b)] = pos[0];
+        if (A.y) A.y[at(j, ld, b)] = pos[1];
+        if (A.yaw) A.yaw[at(j, ld, b)] = atan2(d1[1], d1[0]);
+        if (A.radius) A.radius[at(j, ld, b)] = turn_radius(d1[0], d1[1], d2[0], d2[1]);
+        if (want_chord) {
+            if (j > 0) {
+                if (A.chord_qss) A.chord_qss[at(j - 1, ld, b)] = chord_qss(x_prev, y_prev, pos[0], pos[1]);
+                if (A.chord_norm) A.chord_norm[at(j - 1, ld, b)] = chord_norm(x_prev, y_prev, pos[0], pos[1]);
+            }
+            x_prev = pos[0]; y_prev = pos[1];
+        }
+    }
+    if (want_chord && j1 == N) {  // closing chord N-1 -> 0
+        EvalCursor c0;
+        c0.loaded = -1000;
+        c0.i = 0;
+        eval_at(A, b, c0, A.ts[0], pos, d1, d2);
+        if (A.chord_qss) A.chord_qss[at(N - 1, ld, b)] = chord_qss(x_prev, y_prev, pos[0], pos[1]);
+        if (A.chord_norm) A.chord_norm[at(N - 1, ld, b)] = chord_norm(x_prev, y_prev, pos[0], pos[1]);
     }
 }
+
+STO_HD void eval_candidate(const EvalArgs& A, int b) { eval_range(A, b, 0, A.N); }
 
 // ---- generic degree (1..5), shared knots: one thread per SAMPLE ------------------------------------------
 // scipy _deBoor_D verbatim semantics for any k; used for the track's own splines (k = 3 or 5, smoothing fits

@@ -36,6 +36,20 @@ int hostsim_eval(const double* u, const double* cx, const double* cy, int M, con
     return 0;
 }
 
+// the same with every candidate's sample range split into `split` slices (what the GPU's lane split does)
+int hostsim_eval_split(const double* u, const double* cx, const double* cy, int M, const double* ts, int N, int B, int ld,
+                       int split, double* x, double* y, double* yaw, double* radius, double* chord_qss,
+                       double* chord_norm) {
+    sto::EvalArgs A{u, cx, cy, ts, M, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
+    const int per = (N + split - 1) / split;
+    for (int b = 0; b < B; ++b)
+        for (int g = split - 1; g >= 0; --g) {   // any order: slices are independent
+            const int j0 = g * per, j1 = (j0 + per < N) ? j0 + per : N;
+            sto::eval_range(A, b, j0, j1);
+        }
+    return 0;
+}
+
 int hostsim_eval_spline(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
                         double* x, double* y, double* yaw, double* radius) {
     sto::SplineEvalArgs A{t, cx, cy, ts, nt, k, N, x, y, yaw, radius};

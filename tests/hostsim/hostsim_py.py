@@ -87,13 +87,16 @@ def fit_offsets(cenx, ceny, nrmx, nrmy, offsets):
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 
-def evaluate(u, cx, cy, ts):
+def evaluate(u, cx, cy, ts, split=1):
     u, cx, cy = sm(u), sm(cx), sm(cy)
     M, B = u.shape[0] - 1, u.shape[1]
     ts = np.ascontiguousarray(ts, dtype=np.float64)
     N = len(ts)
-    outs = [np.empty((N, B)) for _ in range(6)]
-    lib().hostsim_eval(_p(u), _p(cx), _p(cy), M, _p(ts), N, B, B, *[_p(o) for o in outs])
+    outs = [np.full((N, B), np.nan) for _ in range(6)]
+    if split == 1:
+        lib().hostsim_eval(_p(u), _p(cx), _p(cy), M, _p(ts), N, B, B, *[_p(o) for o in outs])
+    else:
+        lib().hostsim_eval_split(_p(u), _p(cx), _p(cy), M, _p(ts), N, B, B, int(split), *[_p(o) for o in outs])
     return dict(zip(("x", "y", "yaw", "radius", "chord_qss", "chord_norm"), [o.T.copy() for o in outs]))
 
 

@@ -81,3 +81,15 @@ def test_qss_lane_group_emulation_bit_exact(name, group):
     for k in ("v", "a", "lat", "time"):
         assert np.array_equal(r[k][0], o[k]), k
     assert r["lap"][0] == o["lap"] and r["summary"][0, 6] == o["steps"]
+
+
+@pytest.mark.parametrize("split", [2, 7, 16])
+def test_eval_sample_range_split(split):
+    """Splitting a candidate's samples over lanes (eval_range) gives the same bits as one walk over all of them,
+    including the chords across slice boundaries and the closing chord."""
+    d = golden("cand_m579_n1158")
+    u, cx, cy, _ = H.fit_points(d["points"])
+    whole = H.evaluate(u, cx, cy, d["ts"])
+    parts = H.evaluate(u, cx, cy, d["ts"], split=split)
+    for k in whole:
+        assert np.array_equal(whole[k], parts[k]), k
