@@ -42,6 +42,8 @@ int pick_block(int B) {
     return 128;
 }
 inline int grid_for(int B, int block) { return (B + block - 1) / block; }
+// Lanes per candidate for the fit: 4 (three recurrences + split row work) while the batch leaves SMs idle.
+int pick_fit_split(int B) { return ((long long)B * 4 <= 148LL * 16 * 32) ? 4 : 1; }
 // Lanes per candidate for kernels whose samples are independent: fill ~8 warps per SM before going one-per-candidate.
 int pick_split(int B, int N) {
     int split = 1;
@@ -115,9 +117,13 @@ QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool 
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------
-__global__ void fit_kernel(sto::FitArgs A) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < A.B) sto::fit_candidate(A, b);
+// `split` (a power of two <= 32) lanes share a candidate: per-row work is split over them and the three Thomas
+// recurrences run side by side (sto_fit.cuh).  Whole warps stay alive so the group syncs are warp-uniform.
+__global__ void fit_kernel(sto::FitArgs A, int split) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = t / split, g = t % split;
+    const int lane0 = (threadIdx.x & 31) & ~(split - 1);
+    sto::fit_candidate_lane(A, b < A.B ? b : A.B - 1, b < A.B, g, split, lane0);
 }
 
 // `split` lanes share a candidate, each taking a contiguous slice of its samples (samples are independent): small
@@ -382,8 +388,9 @@ int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, c
     A.cenx = centre_x; A.ceny = centre_y; A.nrmx = normal_x; A.nrmy = normal_y; A.off = offsets;
     A.px = px; A.py = py; A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int block = pick_block(B);
-    fit_kernel<<<grid_for(B, block), block, 0, st>>>(A);
+    const int split = pick_fit_split(B);
+    const int block = pick_block(B * split);
+    fit_kernel<<<grid_for(B * split, block), block, 0, st>>>(A, split);
     STO_CUDA(cudaGetLastError());
     return STO_OK;
 }
@@ -503,7 +510,11 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     F.cenx = centre_x; F.ceny = centre_y; F.nrmx = normal_x; F.nrmy = normal_y; F.off = offsets;
     F.M = M; F.B = B; F.ld = ld; F.u = w.u; F.cx = w.cx; F.cy = w.cy; F.status = status;
     F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz;
-    fit_kernel<<<grid, block, 0, st>>>(F);
+    {
+        const int split = pick_fit_split(B);
+        const int fblock = pick_block(B * split);
+        fit_kernel<<<grid_for(B * split, fblock), fblock, 0, st>>>(F, split);
+    }
     STO_CUDA(cudaGetLastError());
     stage_mark(2, st);
     // lap-only: x, y, yaw are never materialised; the chords and the radius are all the QSS reads

@@ -63,7 +63,7 @@ def sm(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)
 
 
-def fit_points(points):
+def fit_points(points, split=1):
     """points[B, M, 2] -> u[B, M+1], cx[B, M+3], cy[B, M+3], status[B]"""
     pts = np.asarray(points, dtype=np.float64)
     B, M, _ = pts.shape
@@ -71,7 +71,7 @@ def fit_points(points):
     u, cx, cy = np.empty((M + 1, B)), np.empty((M + 3, B)), np.empty((M + 3, B))
     st = np.zeros(B, dtype=np.int32)
     lib().hostsim_fit(None, None, None, None, None, _p(px), _p(py), M, B, B, _p(u), _p(cx), _p(cy),
-                      st.ctypes.data_as(_ip))
+                      st.ctypes.data_as(_ip), int(split))
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 
@@ -83,7 +83,7 @@ def fit_offsets(cenx, ceny, nrmx, nrmy, offsets):
     u, cx, cy = np.empty((M + 1, B)), np.empty((M + 3, B)), np.empty((M + 3, B))
     st = np.zeros(B, dtype=np.int32)
     lib().hostsim_fit(_p(cenx), _p(ceny), _p(nrmx), _p(nrmy), _p(o), None, None, M, B, B, _p(u), _p(cx), _p(cy),
-                      st.ctypes.data_as(_ip))
+                      st.ctypes.data_as(_ip), 1)
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 

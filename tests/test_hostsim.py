@@ -93,3 +93,13 @@ def test_eval_sample_range_split(split):
     parts = H.evaluate(u, cx, cy, d["ts"], split=split)
     for k in whole:
         assert np.array_equal(whole[k], parts[k]), k
+
+
+@pytest.mark.parametrize("split", [2, 4, 5])
+def test_fit_lane_group_phases(split):
+    """The fit split into lane-group phases (row work interleaved over lanes, three Thomas recurrences side by side)
+    produces the same bits as the one-lane fit."""
+    d = golden("cand_m579_n579")
+    u1, cx1, cy1, _ = H.fit_points(d["points"])
+    u2, cx2, cy2, _ = H.fit_points(d["points"], split=split)
+    assert np.array_equal(u1, u2) and np.array_equal(cx1, cx2) and np.array_equal(cy1, cy2)
