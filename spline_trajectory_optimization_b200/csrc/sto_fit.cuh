@@ -193,6 +193,87 @@ STO_HD void fit_phase_backsub(const FitArgs& A, int b, int which) {
     }
 }
 
+// One-lane variants of phases E + F: the three right-hand sides share every pivot, so a single lane runs them in one
+// loop (4 divisions per row instead of 3 x 2).
+STO_HD void fit_phase_thomas_all(const FitArgs& A, int b) {
+    const int M = A.M, ld = A.ld;
+    double beta = 0.0, gamma = 0.0, alpha = 0.0, cpp = 0.0, zxp = 0.0, zyp = 0.0, zzp = 0.0;
+    for (int j0 = 0; j0 < M; j0 += STO_FIT_CHUNK) {
+        double b0s[STO_FIT_CHUNK], b2s[STO_FIT_CHUNK], pxs[STO_FIT_CHUNK], pys[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            b0s[k] = b2s[k] = pxs[k] = pys[k] = 0.0;
+            if (j < M) {
+                b0s[k] = A.cx[at(j, ld, b)];
+                b2s[k] = A.cy[at(j, ld, b)];
+                fit_point(A, j, b, pxs[k], pys[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            if (j >= M) break;
+            const double b0 = b0s[k], b2 = b2s[k];
+            const double b1 = (1.0 - b0) - b2;
+            double den, ncp, nzx, nzy, nzz;
+            if (j == 0) {
+                beta = b0;
+                gamma = -b1;
+                den = b1 - gamma;
+                ncp = b2 / den;
+                nzx = pxs[k] / den;
+                nzy = pys[k] / den;
+                nzz = gamma / den;
+            } else {
+                double dj = b1, wj = 0.0;
+                if (j == M - 1) {
+                    alpha = b2;
+                    dj = b1 - alpha * beta / gamma;
+                    wj = alpha;
+                }
+                den = dj - b0 * cpp;
+                ncp = b2 / den;
+                nzx = (pxs[k] - b0 * zxp) / den;
+                nzy = (pys[k] - b0 * zyp) / den;
+                nzz = (wj - b0 * zzp) / den;
+            }
+            A.cp[at(j, ld, b)] = ncp;
+            A.zx[at(j, ld, b)] = nzx;
+            A.zy[at(j, ld, b)] = nzy;
+            A.zz[at(j, ld, b)] = nzz;
+            cpp = ncp; zxp = nzx; zyp = nzy; zzp = nzz;
+        }
+    }
+}
+STO_HD void fit_phase_backsub_all(const FitArgs& A, int b) {
+    const int M = A.M, ld = A.ld;
+    double zxn = A.zx[at(M - 1, ld, b)], zyn = A.zy[at(M - 1, ld, b)], zzn = A.zz[at(M - 1, ld, b)];
+    for (int j0 = M - 2; j0 >= 0; j0 -= STO_FIT_CHUNK) {
+        double cs[STO_FIT_CHUNK], xs[STO_FIT_CHUNK], ys[STO_FIT_CHUNK], zs[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            cs[k] = xs[k] = ys[k] = zs[k] = 0.0;
+            if (j >= 0) {
+                cs[k] = A.cp[at(j, ld, b)]; xs[k] = A.zx[at(j, ld, b)];
+                ys[k] = A.zy[at(j, ld, b)]; zs[k] = A.zz[at(j, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            if (j < 0) break;
+            zxn = xs[k] - cs[k] * zxn;
+            zyn = ys[k] - cs[k] * zyn;
+            zzn = zs[k] - cs[k] * zzn;
+            A.zx[at(j, ld, b)] = zxn;
+            A.zy[at(j, ld, b)] = zyn;
+            A.zz[at(j, ld, b)] = zzn;
+        }
+    }
+}
+
 // phase G + H: Sherman-Morrison correction, e -> c with the one-slot rotation and the periodic wrap (rows split)
 STO_HD void fit_corner(const FitArgs& A, int b, double& beta, double& gamma) {
     const double b0_first = A.cx[at(0, A.ld, b)], b2_first = A.cy[at(0, A.ld, b)];  // still the b0/b2 scratch
@@ -248,12 +329,12 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
     STO_FIT_SYNC();
     if (active && ok) {
         if (G >= 3) { if (g < 3) fit_phase_thomas(A, b, g); }
-        else if (g == 0) { fit_phase_thomas(A, b, 0); fit_phase_thomas(A, b, 1); fit_phase_thomas(A, b, 2); }
+        else if (g == 0) fit_phase_thomas_all(A, b);
     }
     STO_FIT_SYNC();
     if (active && ok) {
         if (G >= 3) { if (g < 3) fit_phase_backsub(A, b, g); }
-        else if (g == 0) { fit_phase_backsub(A, b, 0); fit_phase_backsub(A, b, 1); fit_phase_backsub(A, b, 2); }
+        else if (g == 0) fit_phase_backsub_all(A, b);
     }
     STO_FIT_SYNC();
     double beta = 0.0, gamma = 1.0;
@@ -270,8 +351,13 @@ STO_HD void fit_candidate(const FitArgs& A, int b, int G = 1) {
     if (!(total > 0.0)) { fit_degenerate(A, b); return; }
     for (int g = 0; g < G; ++g) fit_phase_normalise(A, b, g, G, total);
     for (int g = 0; g < G; ++g) fit_phase_rows(A, b, g, G);
-    for (int w = 0; w < 3; ++w) fit_phase_thomas(A, b, w);
-    for (int w = 0; w < 3; ++w) fit_phase_backsub(A, b, w);
+    if (G >= 3) {
+        for (int w = 0; w < 3; ++w) fit_phase_thomas(A, b, w);
+        for (int w = 0; w < 3; ++w) fit_phase_backsub(A, b, w);
+    } else {
+        fit_phase_thomas_all(A, b);
+        fit_phase_backsub_all(A, b);
+    }
     double beta, gamma;
     fit_corner(A, b, beta, gamma);
     for (int g = 0; g < G; ++g) fit_phase_coefficients(A, b, g, G, beta, gamma);
