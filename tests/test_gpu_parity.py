@@ -292,3 +292,37 @@ def test_long_track_quarter_metre(sto):
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
                             np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=4, ref_pow=0)
     assert not ost.any() and np.array_equal(lap, olap)
+
+
+def test_status_flags_and_chunked_host_path(sto):
+    """Data-dependent failures are per-candidate status bits, never a batch abort; the host entry point chunks a batch
+    to a byte budget without changing a bit."""
+    from spline_trajectory_optimization_b200 import _lib
+    d = golden("cand_m579_n579")
+    veh = _lib.make_vehicle(*veh_args(d))
+    N = len(d["ts"])
+    X, Y, R = d["ref_X"][:3].copy(), d["ref_Y"][:3].copy(), d["ref_CURVATURE"][:3].copy()
+    R[1, 100] = 0.0            # zero turn radius -> zero speed at that sample -> the reference divides by zero (:164-165)
+    X[2, 50] = np.nan          # NaN position -> NaN chord -> NaN segment time
+    for impl in ("plain", "memo"):
+        res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=3, impl=sto.IMPL[impl])
+        st = res["status"][:3].cpu().numpy()
+        lap = res["lap"][:3].cpu().numpy()
+        assert st[0] == 0 and abs(lap[0] - d["ref_lap"][0]) < 1e-9          # the healthy neighbour is untouched
+        assert st[1] & _lib.CAND_ZERO_SPEED and np.isnan(lap[1])
+        assert st[2] != 0 and np.isnan(lap[2])
+    # the single-trajectory mirror raises what the reference raises
+    from spline_traj_optm.models.trajectory import Trajectory
+    from spline_traj_optm.models.vehicle import Vehicle
+    from spline_traj_optm.simulator.simulator import Simulator
+    traj = Trajectory(N)
+    traj[:, Trajectory.X], traj[:, Trajectory.Y], traj[:, Trajectory.CURVATURE] = X[1], Y[1], R[1]
+    with pytest.raises(FloatingPointError):
+        Simulator(Vehicle(test_vehicle_params())).run_simulation(traj)
+    # chunking: a budget that forces several passes over the batch gives the same laps
+    ev = _evaluator(sto, d)
+    lap_one, st_one = ev.lap_times_host(np.tile(d["offsets"], (12, 1)))
+    need32 = ev.lib.sto_lap_workspace_bytes(ev.M, ev.N, 32, ev.impl)
+    lap_chunks, st_chunks = ev.lap_times_host(np.tile(d["offsets"], (12, 1)), max_work_bytes=int(need32 * 1.5) + (4 << 20))
+    assert np.array_equal(lap_one, lap_chunks) and not st_one.any() and not st_chunks.any()
+    assert np.array_equal(lap_one[:8], lap_one[88:])
