@@ -224,6 +224,50 @@ def task_synthetic_tables():
     _save("sim_synthetic_tables", **d)
 
 
+def task_control_points():
+    """The optimiser-loop shape (optimization/optimizer.py:196-211): edit a 5-point window of control points of the
+    s=30,k=5 Monza line, re-impose the periodic wrap, sample_along(ts=...) and run_simulation."""
+    rh.install()
+    from spline_traj_optm.models.trajectory import BSplineTrajectory
+    from spline_traj_optm.models.vehicle import Vehicle
+    base = BSplineTrajectory(rh.load_xy(rh.monza_csv("center")), 30.0, 5)
+    ts = base.sample_along(10.0).ts()
+    rng = np.random.default_rng(99)
+    n = len(base._spl_x.c)
+    B = 6
+    out = {k: [] for k in ("cx", "cy", "X", "Y", "CURVATURE", "SPEED", "TIME", "lap")}
+    edits_idx, edits_xy = [], []
+    for b in range(B):
+        spl = base.copy()
+        start = [7, 20, 33, 46, 59, 70][b]
+        window = list(range(start, start + 5)) if b else []
+        xy = []
+        for idx in window:
+            z = np.array(spl.get_control_point(idx)) + rng.normal(0.0, 1.5, 2)
+            spl.set_control_point(idx, z)
+            xy.append(z)
+        spl.set_control_point(0, spl.get_control_point(-5))      # optimizer.py:201-205
+        spl.set_control_point(1, spl.get_control_point(-4))
+        spl.set_control_point(-3, spl.get_control_point(2))
+        spl.set_control_point(-2, spl.get_control_point(3))
+        spl.set_control_point(-1, spl.get_control_point(4))
+        traj = spl.sample_along(ts=ts)
+        res, scal, _ = rh.simulate(traj)
+        pre = np.array(traj.points)
+        out["cx"].append(np.array(spl._spl_x.c)); out["cy"].append(np.array(spl._spl_y.c))
+        for c in ("X", "Y", "CURVATURE"):
+            out[c].append(pre[:, COLS[c]])
+        out["SPEED"].append(res[:, COLS["SPEED"]]); out["TIME"].append(res[:, COLS["TIME"]])
+        out["lap"].append(res[:, COLS["TIME"]].sum())
+        edits_idx.append(np.array(window + [-1] * (5 - len(window)))); edits_xy.append(np.array(xy + [[0.0, 0.0]] * (5 - len(xy))))
+        print(f"[golden] control points cand {b}: lap {out['lap'][-1]:.9f}", flush=True)
+    d = {"ref_" + k: np.stack(v) for k, v in out.items()}
+    d.update(t=np.array(base._spl_x.t), k=np.int64(5), ts=ts, base_cx=np.array(base._spl_x.c), base_cy=np.array(base._spl_y.c),
+             edit_idx=np.stack(edits_idx), edit_xy=np.stack(edits_xy))
+    d.update({"veh_" + kk: v for kk, v in rh.vehicle_dict(Vehicle(rh.test_vehicle_params())).items()})
+    _save("ctrl_s30k5_n578", **d)
+
+
 TASKS = [
     (task_raw, ()),
     (task_track_splines, ()),
@@ -238,6 +282,7 @@ TASKS = [
     (task_oval, (0.0, "sim_oval_bank0")),
     (task_table_vehicle, ()),
     (task_synthetic_tables, ()),
+    (task_control_points, ()),
     (task_candidates, (10.0, 8, 1, "cand_m579_n579")),
     (task_candidates, (10.0, 3, 2, "cand_m579_n1158")),
     (task_candidates, (2.0, 3, 1, "cand_m2895_n2895")),

@@ -142,6 +142,12 @@ __global__ void eval_spline_kernel(sto::SplineEvalArgs A) {
     if (j < A.N) sto::eval_spline_sample(A, j);
 }
 
+__global__ void eval_spline_batch_kernel(sto::SplineBatchArgs A) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (b < A.B) sto::eval_spline_batch_sample(A, j, b);
+}
+
 // dd / df from explicit x, y columns (the sto_qss_f64 entry); one thread per (sample, candidate)
 __global__ void chord_kernel(const double* x, const double* y, int N, int B, int ld_in, double* dd, double* df,
                              int ld) {
@@ -418,6 +424,24 @@ int sto_sample_spline_f64(const double* t, int nt, const double* cx, const doubl
     return STO_OK;
 }
 
+static int launch_spline_batch(const sto::SplineBatchArgs& A, cudaStream_t st) {
+    const int block = (A.B >= 128) ? 128 : 32;
+    dim3 grid((A.B + block - 1) / block, A.N);
+    eval_spline_batch_kernel<<<grid, block, 0, st>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_sample_splines_f64(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts, int N,
+                           int B, int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
+                           double* chord_norm, void* stream) {
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 1 || B < 1 || ld < B || N > 65535)
+        return fail(STO_ERR_INVALID, "bad spline batch sizes");
+    if (!t || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "t, cx, cy, ts must be non-NULL");
+    sto::SplineBatchArgs A{t, nt, k, cx, cy, ts, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
+    return launch_spline_batch(A, static_cast<cudaStream_t>(stream));
+}
+
 size_t sto_qss_workspace_bytes(int N, int B, int impl) {
     if (N < 2 || B < 1) return 0;
     Carver c(nullptr);
@@ -534,6 +558,39 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     int rc = launch_qss(A, w.qss, vehicle, impl, false, st);
     stage_mark(4, st);
     return rc;
+}
+
+size_t sto_lap_splines_workspace_bytes(int N, int B, int impl) {
+    if (N < 2 || B < 1) return 0;
+    Carver c(nullptr);
+    c.take<double>((size_t)N * ldof(B));
+    carve_qss(c, N, ldof(B), impl, true, true);
+    return c.bytes();
+}
+
+int sto_lap_time_splines_f64(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts,
+                             const double* sin_bank, int N, int B, int ld, const sto_vehicle_f64* vehicle, int impl,
+                             double* lap, int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 2 || N > 65535 || B < 1)
+        return fail(STO_ERR_INVALID, "bad spline batch sizes");
+    if (!t || !cx || !cy || !ts || !lap || !status || !work) return fail(STO_ERR_INVALID, "NULL argument");
+    if (impl != STO_QSS_PLAIN && impl != STO_QSS_MEMO) return fail(STO_ERR_INVALID, "unknown impl");
+    if ((size_t)ld != ldof(B)) return fail(STO_ERR_INVALID, "sto_lap_time_splines_f64 needs ld == round_up(B, 32)");
+    if (int rc = check_vehicle(vehicle)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(work);
+    double* R = c.take<double>((size_t)N * ld);
+    QssWork w = carve_qss(c, N, (size_t)ld, impl, true, true);
+    if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "spline lap workspace too small");
+    zero_status_kernel<<<(B + 255) / 256, 256, 0, st>>>(status, B);
+    sto::SplineBatchArgs E{t, nt, k, cx, cy, ts, N, B, ld, nullptr, nullptr, nullptr, R, w.dd, w.df};
+    if (int rc = launch_spline_batch(E, st)) return rc;
+    sto::QssArgs A{};
+    A.dd = w.dd; A.df = w.df; A.R = R; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = ld; A.cap = w.cap;
+    A.v = w.v; A.a = w.a; A.rec = w.rec; A.rowflag = w.rowflag;
+    A.sp_ent = w.sp_ent; A.sp_ext = w.sp_ext; A.sp_turn = w.sp_turn; A.sp_flag = w.sp_flag;
+    A.lap = lap; A.status = status;
+    return launch_qss(A, w, vehicle, impl, false, st);
 }
 
 int sto_set_stage_timing(int on) {

@@ -272,4 +272,62 @@ STO_HD void eval_spline_sample(const SplineEvalArgs& A, int j) {
     if (A.radius) A.radius[j] = turn_radius(v[2], v[3], v[4], v[5]);
 }
 
+// ---- batch of coefficient sets on SHARED knots (any degree <= 5): one thread per (sample, candidate) -----------------
+// The optimiser-loop shape of the path (reference optimization/optimizer.py:196-211,276-289): many variants of one
+// spline that differ only in control points are resampled at the same parameters.  Knot interval and basis values
+// depend on the sample only; the coefficient loads are coalesced across candidates.
+struct SplineBatchArgs {
+    const double* t;            // [nt] shared knots
+    int nt, k;
+    const double *cx, *cy;      // [nt-k-1][ld] coefficient sets, sample-major
+    const double* ts;           // [N]
+    int N, B, ld;
+    double *x, *y, *yaw, *radius, *chord_qss, *chord_norm;  // [N][ld], each optional
+};
+
+STO_HD int spline_interval(const double* t, int nt, int k, double x) {
+    const int n = nt - k - 1;
+    if (x < t[k + 1] || n - 1 == k) return k;
+    if (x >= t[n - 1]) return n - 1;
+    int lo = k, hi = n - 1;  // t[lo] <= x < t[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= t[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+STO_HD void eval_spline_batch_sample(const SplineBatchArgs& A, int j, int b) {
+    const int k = A.k, ld = A.ld;
+    const double x = A.ts[j];
+    const int ell = spline_interval(A.t, A.nt, k, x);
+    double h[6], v[6];
+    for (int m = 0; m < 3; ++m) {
+        deboor_d(A.t, x, k, ell, m, h);
+        double ax = 0.0, ay = 0.0;
+        for (int a = 0; a <= k; ++a) {
+            ax = ax + A.cx[at(ell + a - k, ld, b)] * h[a];
+            ay = ay + A.cy[at(ell + a - k, ld, b)] * h[a];
+        }
+        v[2 * m] = ax; v[2 * m + 1] = ay;
+    }
+    if (A.x) A.x[at(j, ld, b)] = v[0];
+    if (A.y) A.y[at(j, ld, b)] = v[1];
+    if (A.yaw) A.yaw[at(j, ld, b)] = atan2(v[3], v[2]);
+    if (A.radius) A.radius[at(j, ld, b)] = turn_radius(v[2], v[3], v[4], v[5]);
+    if (A.chord_qss || A.chord_norm) {  // chord j -> j+1 (cyclic): the neighbour's position is re-evaluated here
+        const int jn = (j + 1 == A.N) ? 0 : j + 1;
+        const double xn = A.ts[jn];
+        const int elln = spline_interval(A.t, A.nt, k, xn);
+        deboor_d(A.t, xn, k, elln, 0, h);
+        double bx = 0.0, by = 0.0;
+        for (int a = 0; a <= k; ++a) {
+            bx = bx + A.cx[at(elln + a - k, ld, b)] * h[a];
+            by = by + A.cy[at(elln + a - k, ld, b)] * h[a];
+        }
+        if (A.chord_qss) A.chord_qss[at(j, ld, b)] = chord_qss(v[0], v[1], bx, by);
+        if (A.chord_norm) A.chord_norm[at(j, ld, b)] = chord_norm(v[0], v[1], bx, by);
+    }
+}
+
 }  // namespace sto

@@ -86,6 +86,56 @@ def run_qss(x, y, radius, vehicle, B=None, sin_bank=None, impl=_lib.QSS_MEMO, pr
     return res
 
 
+def lap_times_splines(t, k, cx_sm, cy_sm, ts, vehicle, B=None, sin_bank=None, impl=_lib.QSS_MEMO, work=None):
+    """Batch of coefficient sets on shared knots -> lap times (sto_lap_time_splines_f64).
+
+    t: host knots [nt]; cx_sm, cy_sm: CUDA float64 [nt-k-1, ld] sample-major coefficient sets (one column per
+    candidate), ld == round_up(B, 32); ts: host parameters [N]; sin_bank: host [N] or None.  Per candidate equal to
+    ``spline.sample_along(ts=ts)`` -> ``Simulator(v).run_simulation(traj)`` -> ``sum(TIME)`` with that candidate's
+    control points (reference optimization/optimizer.py:196-211,276-289).  Returns (lap[B], status[B]) device tensors."""
+    lib = _lib.load()
+    n_coef, ld = cx_sm.shape
+    B = ld if B is None else int(B)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    assert n_coef == len(t) - int(k) - 1 and ld == round_up32(B) and cx_sm.dtype == torch.float64
+    dev = cx_sm.device
+    veh = vehicle_struct(vehicle)
+    d_t, d_ts = torch.from_numpy(t).to(dev), torch.from_numpy(ts).to(dev)
+    d_sb = None if sin_bank is None else torch.from_numpy(np.ascontiguousarray(sin_bank, dtype=np.float64)).to(dev)
+    lap = torch.empty(ld, dtype=torch.float64, device=dev)
+    st = torch.empty(ld, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.sto_lap_splines_workspace_bytes(len(ts), B, impl)
+        if work is None or work.numel() < nbytes:
+            work = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sto_lap_time_splines_f64(_ptr(d_t), len(t), int(k), _ptr(cx_sm.contiguous()),
+                                                _ptr(cy_sm.contiguous()), _ptr(d_ts), _ptr(d_sb), len(ts), B, ld,
+                                                C.byref(veh), impl, _ptr(lap), _ptr(st), _ptr(work), work.numel(),
+                                                _stream()))
+        torch.cuda.current_stream().synchronize()   # d_t / d_ts / d_sb are temporaries of this call
+    return lap[:B], st[:B]
+
+
+def sample_splines(t, k, cx_sm, cy_sm, ts, B=None, want=("x", "y", "yaw", "radius")):
+    """sample_along(ts=...) for a batch of coefficient sets on shared knots (sto_sample_splines_f64)."""
+    lib = _lib.load()
+    n_coef, ld = cx_sm.shape
+    B = ld if B is None else int(B)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    dev = cx_sm.device
+    d_t, d_ts = torch.from_numpy(t).to(dev), torch.from_numpy(ts).to(dev)
+    names = ("x", "y", "yaw", "radius", "chord_qss", "chord_norm")
+    out = {n: (torch.empty((len(ts), ld), dtype=torch.float64, device=dev) if n in want else None) for n in names}
+    with torch.cuda.device(dev):
+        _lib.check(lib.sto_sample_splines_f64(_ptr(d_t), len(t), int(k), _ptr(cx_sm.contiguous()),
+                                              _ptr(cy_sm.contiguous()), _ptr(d_ts), len(ts), B, ld,
+                                              *[_ptr(out[n]) for n in names], _stream()))
+        torch.cuda.current_stream().synchronize()
+    return {n: v for n, v in out.items() if v is not None}
+
+
 class BatchedLineEvaluator:
     def __init__(self, centre_xy, left_normal_xy, ts, vehicle, bank=None, device=None, impl="memo"):
         """centre_xy, left_normal_xy: [M, 2] host arrays; ts: [N] spline parameters in [0, 1);

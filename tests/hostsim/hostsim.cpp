@@ -50,6 +50,15 @@ int hostsim_eval_split(const double* u, const double* cx, const double* cy, int 
     return 0;
 }
 
+int hostsim_eval_spline_batch(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts, int N,
+                              int B, int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
+                              double* chord_norm) {
+    sto::SplineBatchArgs A{t, nt, k, cx, cy, ts, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
+    for (int j = 0; j < N; ++j)
+        for (int b = 0; b < B; ++b) sto::eval_spline_batch_sample(A, j, b);
+    return 0;
+}
+
 int hostsim_eval_spline(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
                         double* x, double* y, double* yaw, double* radius) {
     sto::SplineEvalArgs A{t, cx, cy, ts, nt, k, N, x, y, yaw, radius};

@@ -100,6 +100,16 @@ def evaluate(u, cx, cy, ts, split=1):
     return dict(zip(("x", "y", "yaw", "radius", "chord_qss", "chord_norm"), [o.T.copy() for o in outs]))
 
 
+def eval_spline_batch(t, k, cx, cy, ts):
+    """cx, cy: [B, n_coef] -> dict of [B, N] arrays"""
+    t, ts = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, ts))
+    cxs, cys = sm(cx), sm(cy)
+    B, N = cxs.shape[1], len(ts)
+    outs = [np.empty((N, B)) for _ in range(6)]
+    lib().hostsim_eval_spline_batch(_p(t), len(t), int(k), _p(cxs), _p(cys), _p(ts), N, B, B, *[_p(o) for o in outs])
+    return dict(zip(("x", "y", "yaw", "radius", "chord_qss", "chord_norm"), [o.T.copy() for o in outs]))
+
+
 def eval_spline(t, cx, cy, k, ts):
     t, cx, cy, ts = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, cx, cy, ts))
     N = len(ts)

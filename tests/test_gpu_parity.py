@@ -326,3 +326,21 @@ def test_status_flags_and_chunked_host_path(sto):
     lap_chunks, st_chunks = ev.lap_times_host(np.tile(d["offsets"], (12, 1)), max_work_bytes=int(need32 * 1.5) + (4 << 20))
     assert np.array_equal(lap_one, lap_chunks) and not st_one.any() and not st_chunks.any()
     assert np.array_equal(lap_one[:8], lap_one[88:])
+
+
+def test_control_point_variants_batched(sto):
+    """§8 f-2 (optimiser-loop batching): the reference's edit -> wrap -> sample_along(ts) -> run_simulation sequence for
+    six control-point variants of the s=30,k=5 Monza line, scored in one launch."""
+    from spline_trajectory_optimization_b200 import tracks
+    from spline_trajectory_optimization_b200.models.trajectory import BSplineTrajectory
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    from spline_trajectory_optimization_b200.optimization.batched import score_control_point_variants
+    d = golden("ctrl_s30k5_n578")
+    spl = BSplineTrajectory(tracks.monza_raw()[0], 30.0, 5)
+    edits = [{int(i): tuple(xy) for i, xy in zip(idx, xys) if i >= 0} for idx, xys in zip(d["edit_idx"], d["edit_xy"])]
+    lap, st = score_control_point_variants(spl, edits, d["ts"], Vehicle(test_vehicle_params()))
+    assert not st.any()
+    assert np.max(np.abs(lap - d["ref_lap"])) < 1e-9          # identical inputs (same coefficients): 1e-9 s
+    S = sto.sample_splines(d["t"], int(d["k"]), to_sm(d["ref_cx"]), to_sm(d["ref_cy"]), d["ts"], B=6)
+    assert np.array_equal(to_cm(S["x"], 6), d["ref_X"]) and np.array_equal(to_cm(S["y"], 6), d["ref_Y"])
+    assert rel_err(to_cm(S["radius"], 6), d["ref_CURVATURE"]) < 1e-15

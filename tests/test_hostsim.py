@@ -103,3 +103,32 @@ def test_fit_lane_group_phases(split):
     u1, cx1, cy1, _ = H.fit_points(d["points"])
     u2, cx2, cy2, _ = H.fit_points(d["points"], split=split)
     assert np.array_equal(u1, u2) and np.array_equal(cx1, cx2) and np.array_equal(cy1, cy2)
+
+
+def test_spline_batch_shared_knots():
+    """Coefficient sets on shared knots (the optimiser-loop shape): samples bit-identical to the reference's
+    sample_along(ts=...) after set_control_point edits, chords consistent with the per-candidate evaluator."""
+    d = golden("ctrl_s30k5_n578")
+    E = H.eval_spline_batch(d["t"], int(d["k"]), d["ref_cx"], d["ref_cy"], d["ts"])
+    assert np.array_equal(E["x"], d["ref_X"]) and np.array_equal(E["y"], d["ref_Y"])
+    assert np.max(np.abs(E["radius"] - d["ref_CURVATURE"]) / d["ref_CURVATURE"]) < 1e-15
+    nxt = np.roll(E["x"], -1, axis=1), np.roll(E["y"], -1, axis=1)
+    assert np.array_equal(E["chord_qss"], np.sqrt((E["x"] - nxt[0]) ** 2 + (E["y"] - nxt[1]) ** 2))
+    hv, ov = H.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    r = H.qss(1, E["x"], E["y"], E["radius"], None, hv)
+    for b in range(E["x"].shape[0]):
+        o = O.qss(E["x"][b], E["y"][b], E["radius"][b], np.zeros(E["x"].shape[1]), ov, 0)
+        assert np.array_equal(r["v"][b], o["v"]) and r["lap"][b] == o["lap"]
+        assert abs(r["lap"][b] - d["ref_lap"][b]) < 1e-9
+
+
+def test_control_point_variants_match_reference_edits():
+    from spline_trajectory_optimization_b200.optimization.batched import control_point_variants
+    from spline_trajectory_optimization_b200.models.trajectory import BSplineTrajectory
+    from spline_trajectory_optimization_b200 import tracks
+    d = golden("ctrl_s30k5_n578")
+    spl = BSplineTrajectory(tracks.monza_raw()[0], 30.0, 5)
+    assert np.array_equal(spl._spl_x.c, d["base_cx"])
+    edits = [{int(i): tuple(xy) for i, xy in zip(idx, xys) if i >= 0} for idx, xys in zip(d["edit_idx"], d["edit_xy"])]
+    cx, cy = control_point_variants(spl, edits)
+    assert np.array_equal(cx, d["ref_cx"]) and np.array_equal(cy, d["ref_cy"])
