@@ -119,6 +119,13 @@ int sto_sample_f64(const double* u, const double* cx, const double* cy, int M, c
 int sto_sample_spline_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts,
                           int N, double* x, double* y, double* yaw, double* radius, void* stream);
 
+/* Arc length of the sample intervals of one spline: sec[0] = 0, sec[i] = integral of |r'(t)| over [ts[i-1], ts[i]]
+ * (what sample_along accumulates into DIST_TO_SF_BWD with one adaptive quad call per sample,
+ * models/trajectory.py:228-230,283-289).  Fixed 8-point Gauss-Legendre per knot span: agrees with quad to its own
+ * tolerance (~1e-8 relative; measured ~1e-12).  All pointers DEVICE; the caller accumulates. */
+int sto_arc_sections_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
+                         double* sec, void* stream);
+
 /* Batch of coefficient sets on SHARED knots (any degree 1..5): the optimiser-loop shape of the path - the reference's
  * TrajectoryOptimizer edits control points of one spline and calls sample_along(ts=...) + run_simulation after every
  * edit (optimization/optimizer.py:196-211,276-289).  t[nt], ts[N] shared; cx, cy [nt-k-1][ld] sample-major; outputs as

@@ -148,6 +148,11 @@ __global__ void eval_spline_batch_kernel(sto::SplineBatchArgs A) {
     if (b < A.B) sto::eval_spline_batch_sample(A, j, b);
 }
 
+__global__ void arc_sections_kernel(sto::ArcArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.N) sto::arc_section(A, i);
+}
+
 // dd / df from explicit x, y columns (the sto_qss_f64 entry); one thread per (sample, candidate)
 __global__ void chord_kernel(const double* x, const double* y, int N, int B, int ld_in, double* dd, double* df,
                              int ld) {
@@ -440,6 +445,16 @@ int sto_sample_splines_f64(const double* t, int nt, int k, const double* cx, con
     if (!t || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "t, cx, cy, ts must be non-NULL");
     sto::SplineBatchArgs A{t, nt, k, cx, cy, ts, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
     return launch_spline_batch(A, static_cast<cudaStream_t>(stream));
+}
+
+int sto_arc_sections_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
+                         double* sec, void* stream) {
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 1) return fail(STO_ERR_INVALID, "bad spline sizes");
+    if (!t || !cx || !cy || !ts || !sec) return fail(STO_ERR_INVALID, "NULL argument");
+    sto::ArcArgs A{t, cx, cy, ts, nt, k, N, sec};
+    arc_sections_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
 }
 
 size_t sto_qss_workspace_bytes(int N, int B, int impl) {

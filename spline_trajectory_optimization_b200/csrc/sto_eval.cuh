@@ -330,4 +330,52 @@ STO_HD void eval_spline_batch_sample(const SplineBatchArgs& A, int j, int b) {
     }
 }
 
+// ---- arc length of the sample intervals (DIST_TO_SF_BWD / FWD columns), one spline, one thread per interval ----------
+// The reference integrates |r'(t)| over [ts[i-1], ts[i]] with adaptive QUADPACK, one Python call per sample
+// (models/trajectory.py:228-230,283-289; >99 % of sample_along's time, and the QSS never reads the result).  Here each
+// interval is split at the knots it contains and every piece (where x', y' are polynomials) gets a fixed 8-point
+// Gauss-Legendre rule: ~1e-13 relative quadrature error, i.e. agreement with quad at its own tolerance (1.5e-8).
+struct ArcArgs {
+    const double *t, *cx, *cy, *ts;
+    int nt, k, N;
+    double* sec;  // [N]: sec[0] = 0, sec[i] = length of the curve between ts[i-1] and ts[i]
+};
+
+STO_HD double spline_speed(const ArcArgs& A, double x) {
+    const int k = A.k;
+    const int ell = spline_interval(A.t, A.nt, k, x);
+    double h[6];
+    deboor_d(A.t, x, k, ell, 1, h);
+    double dx = 0.0, dy = 0.0;
+    for (int a = 0; a <= k; ++a) {
+        dx = dx + A.cx[ell + a - k] * h[a];
+        dy = dy + A.cy[ell + a - k] * h[a];
+    }
+    return sqrt(dx * dx + dy * dy);
+}
+
+STO_HD void arc_section(const ArcArgs& A, int i) {
+    if (i == 0) { A.sec[0] = 0.0; return; }
+    // 8-point Gauss-Legendre nodes / weights on [-1, 1]
+    const double gx[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+    const double gw[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+    const double a = A.ts[i - 1], b = A.ts[i];
+    const int n = A.nt - A.k - 1;
+    double total = 0.0, lo = a;
+    int ell = spline_interval(A.t, A.nt, A.k, a);
+    while (lo < b) {
+        double hi = b;
+        if (ell + 1 <= n - 1 && A.t[ell + 1] < b) hi = A.t[ell + 1];   // stop at the next knot inside the interval
+        if (hi <= lo) { ++ell; if (ell > n - 1) break; continue; }
+        const double c = 0.5 * (lo + hi), hw = 0.5 * (hi - lo);
+        double acc = 0.0;
+        for (int q = 0; q < 4; ++q)
+            acc += gw[q] * (spline_speed(A, c - hw * gx[q]) + spline_speed(A, c + hw * gx[q]));
+        total += hw * acc;
+        lo = hi;
+        ++ell;
+    }
+    A.sec[i] = total;
+}
+
 }  // namespace sto

@@ -50,6 +50,13 @@ int hostsim_eval_split(const double* u, const double* cx, const double* cy, int 
     return 0;
 }
 
+int hostsim_arc_sections(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,
+                         double* sec) {
+    sto::ArcArgs A{t, cx, cy, ts, nt, k, N, sec};
+    for (int i = 0; i < N; ++i) sto::arc_section(A, i);
+    return 0;
+}
+
 int hostsim_eval_spline_batch(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts, int N,
                               int B, int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
                               double* chord_norm) {

@@ -100,6 +100,13 @@ def evaluate(u, cx, cy, ts, split=1):
     return dict(zip(("x", "y", "yaw", "radius", "chord_qss", "chord_norm"), [o.T.copy() for o in outs]))
 
 
+def arc_sections(t, cx, cy, k, ts):
+    t, cx, cy, ts = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, cx, cy, ts))
+    sec = np.empty(len(ts))
+    lib().hostsim_arc_sections(_p(t), len(t), _p(cx), _p(cy), int(k), _p(ts), len(ts), _p(sec))
+    return sec
+
+
 def eval_spline_batch(t, k, cx, cy, ts):
     """cx, cy: [B, n_coef] -> dict of [B, N] arrays"""
     t, ts = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, ts))

@@ -175,6 +175,11 @@ def test_bspline_trajectory_sample_along_on_device(sto):
     assert rel_err(traj[:, Trajectory.CURVATURE], d["in_CURVATURE"]) < 1e-15
     assert np.max(np.abs(traj[:, Trajectory.YAW] - d["in_YAW"])) < 1e-14
     assert np.allclose(traj[:, Trajectory.DIST_TO_SF_BWD], d["in_DIST_BWD"], rtol=1e-12)
+    # the GPU's fixed-order quadrature for the same columns (models/trajectory.py:283-289)
+    fast = spl.sample_along(10.0, arc_length="gauss")
+    assert np.allclose(fast[1:, Trajectory.DIST_TO_SF_BWD], d["in_DIST_BWD"][1:], rtol=1e-9, atol=0)
+    assert np.allclose(fast[:, Trajectory.DIST_TO_SF_FWD], d["in_DIST_FWD"], rtol=1e-9, atol=0)
+    assert np.array_equal(fast[:, Trajectory.X], d["in_X"])
 
 
 def test_edge_cases(sto):

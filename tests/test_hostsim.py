@@ -132,3 +132,14 @@ def test_control_point_variants_match_reference_edits():
     edits = [{int(i): tuple(xy) for i, xy in zip(idx, xys) if i >= 0} for idx, xys in zip(d["edit_idx"], d["edit_xy"])]
     cx, cy = control_point_variants(spl, edits)
     assert np.array_equal(cx, d["ref_cx"]) and np.array_equal(cy, d["ref_cy"])
+
+
+@pytest.mark.parametrize("name", ["sim_s30k5_i10", "sim_s10k3_i2", "sim_s0k3_i10"])
+def test_arc_sections_gauss_legendre(name):
+    """DIST_TO_SF_BWD from fixed-order Gauss-Legendre per knot span vs the reference's adaptive quad (its own tolerance
+    is 1.5e-8 relative): <= 1e-9 relative."""
+    d = golden(name)
+    sec = H.arc_sections(d["spl_t"], d["spl_cx"], d["spl_cy"], int(d["spl_k"]), d["ts"])
+    bwd = np.cumsum(sec)
+    assert bwd[0] == 0.0
+    assert np.max(np.abs(bwd[1:] - d["in_DIST_BWD"][1:]) / d["in_DIST_BWD"][1:]) < 1e-9
