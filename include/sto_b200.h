@@ -119,6 +119,13 @@ int sto_sample_f64(const double* u, const double* cx, const double* cy, int M, c
 int sto_sample_spline_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts,
                           int N, double* x, double* y, double* yaw, double* radius, void* stream);
 
+/* Trajectory.fill_bounds (models/trajectory.py:83-141; RaceTrack.fill_trajectory_boundaries, models/race_track.py:98-104):
+ * for each point P_i with unit normal n_i, the nearest intersection of the segment P_i -/+ max_dist * n_i with the closed
+ * polyline ring_xy[m][2] (closed implicitly); no intersection -> the point itself (found[i] = 0).  All pointers DEVICE. */
+int sto_fill_bounds_f64(const double* px, const double* py, const double* nx, const double* ny, int n,
+                        const double* ring_xy, int m, double max_dist, double* bx, double* by, int32_t* found,
+                        void* stream);
+
 /* Arc length of the sample intervals of one spline: sec[0] = 0, sec[i] = integral of |r'(t)| over [ts[i-1], ts[i]]
  * (what sample_along accumulates into DIST_TO_SF_BWD with one adaptive quad call per sample,
  * models/trajectory.py:228-230,283-289).  Fixed 8-point Gauss-Legendre per knot span: agrees with quad to its own

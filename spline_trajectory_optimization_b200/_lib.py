@@ -42,6 +42,7 @@ _SIGNATURES = {
     "sto_fit_periodic_cubic_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [_vp] * 4 + [_vp, C.c_size_t, _vp]),
     "sto_sample_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int] + [_vp] * 6 + [_vp]),
     "sto_sample_spline_f64": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int] + [_vp] * 4 + [_vp]),
+    "sto_fill_bounds_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
     "sto_arc_sections_f64": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "sto_sample_splines_f64": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int] + [_vp] * 6 + [_vp]),
     "sto_lap_splines_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

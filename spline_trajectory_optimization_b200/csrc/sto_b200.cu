@@ -148,6 +148,33 @@ __global__ void eval_spline_batch_kernel(sto::SplineBatchArgs A) {
     if (b < A.B) sto::eval_spline_batch_sample(A, j, b);
 }
 
+// Trajectory.fill_bounds (reference models/trajectory.py:83-141): nearest intersection of the two-sided segment
+// P -/+ max_dist * n with a closed polyline; no hit -> the point itself.  One thread per point, edges streamed from L1/L2.
+__global__ void fill_bounds_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                   const double* __restrict__ nx, const double* __restrict__ ny, int n,
+                                   const double* __restrict__ ring, int m, double max_dist, double* bx, double* by,
+                                   int32_t* found) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double Px = px[i], Py = py[i], dx = nx[i], dy = ny[i];
+    double best = INFINITY, tbest = 0.0;
+    for (int j = 0; j < m; ++j) {
+        const int jn = (j + 1 == m) ? 0 : j + 1;
+        const double ax = ring[2 * j], ay = ring[2 * j + 1];
+        const double ex = ring[2 * jn] - ax, ey = ring[2 * jn + 1] - ay;
+        const double wx = ax - Px, wy = ay - Py;
+        const double den = dx * ey - dy * ex;
+        if (den == 0.0) continue;
+        const double t = (wx * ey - wy * ex) / den;   // along the normal
+        const double s = (wx * dy - wy * dx) / den;   // along the edge
+        if (s >= 0.0 && s <= 1.0 && fabs(t) <= max_dist && fabs(t) < best) { best = fabs(t); tbest = t; }
+    }
+    const bool hit = best < INFINITY;
+    bx[i] = hit ? Px + tbest * dx : Px;
+    by[i] = hit ? Py + tbest * dy : Py;
+    if (found) found[i] = hit ? 1 : 0;
+}
+
 __global__ void arc_sections_kernel(sto::ArcArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < A.N) sto::arc_section(A, i);
@@ -445,6 +472,17 @@ int sto_sample_splines_f64(const double* t, int nt, int k, const double* cx, con
     if (!t || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "t, cx, cy, ts must be non-NULL");
     sto::SplineBatchArgs A{t, nt, k, cx, cy, ts, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
     return launch_spline_batch(A, static_cast<cudaStream_t>(stream));
+}
+
+int sto_fill_bounds_f64(const double* px, const double* py, const double* nx, const double* ny, int n,
+                        const double* ring_xy, int m, double max_dist, double* bx, double* by, int32_t* found,
+                        void* stream) {
+    if (n < 1 || m < 2 || !px || !py || !nx || !ny || !ring_xy || !bx || !by)
+        return fail(STO_ERR_INVALID, "bad fill_bounds arguments");
+    fill_bounds_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(px, py, nx, ny, n, ring_xy, m,
+                                                                                     max_dist, bx, by, found);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
 }
 
 int sto_arc_sections_f64(const double* t, int nt, const double* cx, const double* cy, int k, const double* ts, int N,

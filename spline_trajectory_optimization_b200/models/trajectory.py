@@ -71,6 +71,31 @@ def _ray_ring_hits(points, normals, ring, max_dist):
     return hit, found
 
 
+def _device_ray_ring_hits(points, normals, ring, max_dist):
+    """GPU version of _ray_ring_hits (sto_fill_bounds_f64); None when no CUDA device is visible."""
+    try:
+        import torch
+    except ImportError:  # pragma: no cover
+        return None
+    if not torch.cuda.is_available():
+        return None
+    from .. import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = np.asarray(ring, dtype=np.float64)
+    if np.array_equal(a[0], a[-1]):
+        a = a[:-1]
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    px, py, nx, ny, rg = up(points[:, 0]), up(points[:, 1]), up(normals[:, 0]), up(normals[:, 1]), up(a)
+    n = len(points)
+    out = torch.empty((2, n), dtype=torch.float64, device=dev)
+    found = torch.empty(n, dtype=torch.int32, device=dev)
+    _lib.check(lib.sto_fill_bounds_f64(px.data_ptr(), py.data_ptr(), nx.data_ptr(), ny.data_ptr(), n, rg.data_ptr(),
+                                       len(a), float(max_dist), out[0].data_ptr(), out[1].data_ptr(), found.data_ptr(),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.T.cpu().numpy(), found.cpu().numpy().astype(bool)
+
+
 class Trajectory:
     X = 0
     Y = 1
@@ -131,9 +156,10 @@ class Trajectory:
         return np.linspace(0.0, 1.0, len(self), endpoint=False)
 
     # ---- bounds / regions (NumPy restatement of the shapely queries) ------------------------------------------
-    def fill_bounds(self, left_poly, right_poly, max_dist=100.0):
+    def fill_bounds(self, left_poly, right_poly, max_dist=100.0, device=True):
         """left_poly / right_poly: [m, 2] vertex arrays of the closed boundary polylines (anything with a
-        ``coords`` attribute, e.g. a shapely LinearRing, is accepted too)."""
+        ``coords`` attribute, e.g. a shapely LinearRing, is accepted too).  Runs on the GPU when one is visible
+        (same arithmetic as the NumPy path, bit-identical results); device=False forces NumPy."""
         def verts(poly):
             return np.asarray(poly.coords if hasattr(poly, "coords") else poly, dtype=np.float64)[:, :2]
         P = self.points[:, [Trajectory.X, Trajectory.Y]]
@@ -141,7 +167,8 @@ class Trajectory:
         for poly, norm, cx, cy in ((left_poly, np.pi / 2.0, Trajectory.LEFT_BOUND_X, Trajectory.LEFT_BOUND_Y),
                                    (right_poly, -np.pi / 2.0, Trajectory.RIGHT_BOUND_X, Trajectory.RIGHT_BOUND_Y)):
             n = np.stack([np.cos(yaw + norm), np.sin(yaw + norm)], axis=1)
-            hit, _ = _ray_ring_hits(P, n, verts(poly), max_dist)
+            res = _device_ray_ring_hits(P, n, verts(poly), max_dist) if device else None
+            hit, _ = res if res is not None else _ray_ring_hits(P, n, verts(poly), max_dist)
             self.points[:, cx] = hit[:, 0]
             self.points[:, cy] = hit[:, 1]
 

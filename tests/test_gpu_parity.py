@@ -349,3 +349,23 @@ def test_control_point_variants_batched(sto):
     S = sto.sample_splines(d["t"], int(d["k"]), to_sm(d["ref_cx"]), to_sm(d["ref_cy"]), d["ts"], B=6)
     assert np.array_equal(to_cm(S["x"], 6), d["ref_X"]) and np.array_equal(to_cm(S["y"], 6), d["ref_Y"])
     assert rel_err(to_cm(S["radius"], 6), d["ref_CURVATURE"]) < 1e-15
+
+
+def test_fill_bounds_on_device(sto):
+    """§8 f-1: Trajectory.fill_bounds on the GPU == its NumPy restatement (bit for bit) on the Monza track."""
+    from spline_trajectory_optimization_b200 import tracks
+    from spline_trajectory_optimization_b200.models.race_track import RaceTrack
+    from spline_trajectory_optimization_b200.models.trajectory import Trajectory
+    c, l, r = tracks.monza_raw()
+    rt = RaceTrack("monza", l, r, c, s=10.0, interval=5.0)       # constructor already used the device path
+    host = rt.center_d.copy()
+    host[:, Trajectory.LEFT_BOUND_X:Trajectory.RIGHT_BOUND_Y + 1] = 0.0
+    host.fill_bounds(rt.left_r, rt.right_r, max_dist=100.0, device=False)
+    cols = slice(Trajectory.LEFT_BOUND_X, Trajectory.RIGHT_BOUND_Y + 1)
+    assert np.array_equal(host[:, cols], rt.center_d[:, cols])
+    assert 3.0 < rt.dist_to_left.min() and rt.dist_to_left.max() < 7.5 and 3.0 < rt.dist_to_right.min()
+    # a point with no boundary within max_dist keeps itself as its bound (reference :118-127)
+    far = Trajectory(1)
+    far[0, Trajectory.X], far[0, Trajectory.Y] = 1e5, 1e5
+    far.fill_bounds(rt.left_r, rt.right_r, max_dist=100.0)
+    assert far[0, Trajectory.LEFT_BOUND_X] == 1e5 and far[0, Trajectory.RIGHT_BOUND_Y] == 1e5
