@@ -178,7 +178,7 @@ def test_bspline_trajectory_sample_along_on_device(sto):
     # the GPU's fixed-order quadrature for the same columns (models/trajectory.py:283-289)
     fast = spl.sample_along(10.0, arc_length="gauss")
     assert np.allclose(fast[1:, Trajectory.DIST_TO_SF_BWD], d["in_DIST_BWD"][1:], rtol=1e-9, atol=0)
-    assert np.allclose(fast[:, Trajectory.DIST_TO_SF_FWD], d["in_DIST_FWD"], rtol=1e-9, atol=0)
+    assert np.allclose(fast[:, Trajectory.DIST_TO_SF_FWD], d["in_DIST_FWD"], rtol=0, atol=1e-6)   # metres of 5.8 km
     assert np.array_equal(fast[:, Trajectory.X], d["in_X"])
 
 
