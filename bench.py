@@ -309,7 +309,12 @@ def run_gpu_arm(args):
             "kernels_per_step": ["zero_status_kernel", "fit_kernel", "eval_kernel",
                                  "qss_memo_kernel" if args.qss == "memo" else "qss_plain_kernel", "argmin_kernel"],
             "roofline": {"bound": "hbm", "kernel": "qss_%s_kernel" % args.qss, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one qss_memo_kernel<4> launch at this
+                         # workload, from profiles/r01_qss_memo_final_ncu_summary.txt (ncu --set full); not live
+                         "traffic": (3.756e9 if (args.qss == "memo" and B == CANDIDATES_PER_GPU) else None),
+                         "traffic_source": "ncu --set full capture, profiles/r01_qss_memo_final_ncu_summary.txt",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_candidate": 8 * M + 8, "kernel_ms": qss_ms,
                          "stage_ms": {"status": float(stage_ms[0]), "fit": float(stage_ms[1]),
                                       "sample": float(stage_ms[2]), "qss": qss_ms},
