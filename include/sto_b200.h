@@ -15,6 +15,8 @@
  *   - All arithmetic is FP64.  Device arrays are structure-of-arrays, SAMPLE-MAJOR: element (i, b) of an
  *     [n][B] array lives at ptr[i * ld + b] with ld >= B the leading dimension in elements (candidates are
  *     the contiguous axis, so one warp = 32 neighbouring candidates reads one 256-byte line per sample).
+ *     The QSS / fused entry points (sto_qss_f64, sto_lap_time_f64, sto_lap_time_splines_f64) require
+ *     ld == round_up(B, 32) exactly (their workspaces are carved with that leading dimension).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points
  *     enqueue work and return without synchronising; host-buffer entry points (suffix _host) synchronise
  *     the stream before returning because their outputs live in caller memory.

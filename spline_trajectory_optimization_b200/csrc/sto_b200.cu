@@ -43,7 +43,17 @@ int pick_block(int B) {
 }
 inline int grid_for(int B, int block) { return (B + block - 1) / block; }
 // Lanes per candidate for the fit: 4 (three recurrences + split row work) while the batch leaves SMs idle.
-int pick_fit_split(int B) { return ((long long)B * 4 <= 148LL * 16 * 32) ? 4 : 1; }
+int pick_fit_split(int B) {
+    if (const char* e = getenv("STO_FIT_SPLIT")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
+    }
+    // measured on B200 (Monza, M = 2895): 4,096 candidates 10.2 / 7.6 / 5.5 / 4.5 / 4.4 ms at 1 / 2 / 4 / 8 / 16 lanes;
+    // 32,768 candidates 12.1 / 9.5 / 12.8 / 20.0 ms at 1 / 2 / 4 / 8 lanes
+    if ((long long)B * 8 <= 148LL * 8 * 32) return 8;
+    if (B <= 16384) return 4;
+    return 2;
+}
 // Lanes per candidate for kernels whose samples are independent: fill ~8 warps per SM before going one-per-candidate.
 int pick_split(int B, int N) {
     int split = 1;
