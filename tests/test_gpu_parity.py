@@ -161,6 +161,11 @@ def test_simulator_drop_in(sto):
     assert np.allclose(got, ref, rtol=1e-11, atol=0)
     assert abs(res.lap_time - float(d["lap"])) < 1e-9
     assert "Lap Time" in str(res)
+    # the fast variant (memoised kernel): same profile bit for bit, ITERATION_FLAG not tracked
+    fast = Simulator(Vehicle(test_vehicle_params()), track_iteration_flag=False).run_simulation(traj, False)
+    for c in (Trajectory.SPEED, Trajectory.LON_ACC, Trajectory.LAT_ACC, Trajectory.TIME):
+        assert np.array_equal(fast.trajectory[:, c], out[:, c])
+    assert (fast.trajectory[:, Trajectory.ITERATION_FLAG] == -1).all() and fast.lap_time == res.lap_time
 
 
 def test_bspline_trajectory_sample_along_on_device(sto):
