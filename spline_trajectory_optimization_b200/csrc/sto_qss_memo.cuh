@@ -455,25 +455,58 @@ STO_HD void memo_bwd_rows_group(const QssArgs& A, const MemoWork& W, const MemoC
             else res = eval_pure(A, V, b, false, p, q, lat0);
         }
         __syncwarp();
-        // commit in row order; every lane of the group mirrors the bookkeeping
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-            int flags = 0;
-            if (g == k && res.kind != EV_NONE) {
-                bool spawn, changed;
-                int st = 0;
-                const bool stopped = apply_res(A, C, b, false, p, q, res, st, spawn, changed);
-                if (spawn) memo_spawn(A, W, b, q, s, nB, nnew, st);
-                flags = (stopped ? 1 : 0) | (spawn ? 2 : 0) | (st << 2);
-            }
-            __syncwarp();
-            flags = __shfl_sync(0xffffffffu, flags, lane0 + k);
-            if (k < n) {
-                if (flags & 1) { L &= ~(1ull << kth_bit(att, k)); --nlive; }
-                if (flags & 2) ++nnew;
-                status |= flags >> 2;
-            }
+        // Commit, all lanes at once.  Sequentially (row order) token k would: clear the memos around q_k, then set its
+        // own edge's memo at p_k.  Inside one batch the only interaction is that the NEXT row, if adjacent and
+        // state-changing, clears the bit token k just set (its q is p_k).  So: phase 1 = state write + own-edge memo,
+        // phase 2 = the invalidation clears minus the own edge (shared-memory atomics; different tokens may hit the
+        // same word).  Equivalent to the ordered commit the host emulation performs.
+        const bool has = res.kind != EV_NONE;
+        const bool stopped = has && (res.kind == EV_KILL || res.kind == EV_STOP || res.kind == EV_SPAWN ||
+                                     res.kind == EV_RESPAWN || res.kind == EV_ZERO);
+        const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
+        const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
+        const u64 pbit = 1ull << (p & 63);
+        u64* const contw = cont.m + (size_t)(p >> 6) * cont.stride;
+        u64* const stopw = stop.m + (size_t)(p >> 6) * stop.stride;
+        if (changed) {
+            double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
+            rq[0] = res.v_new;
+            rq[1] = res.a_new;
         }
+        if (has) {
+            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atomicOr(contw, pbit); atomicAnd(stopw, ~pbit); }
+            else if (res.kind == EV_STOP) { atomicOr(stopw, pbit); atomicAnd(contw, ~pbit); }
+            else if (res.kind == EV_SPAWN) { atomicAnd(contw, ~pbit); atomicAnd(stopw, ~pbit); }
+            if (stopped) atomicAnd(live.m + (size_t)w * live.stride, ~(1ull << kth_bit(att, g)));
+        }
+        __syncwarp();
+        if (changed) {
+            const int qp = (q == 0) ? N - 1 : q - 1;
+            const u64 qbit = 1ull << (q & 63);
+            atomicAnd(cont.m + (size_t)(q >> 6) * cont.stride, ~qbit);            // edge q -> q-1
+            atomicAnd(stop.m + (size_t)(q >> 6) * stop.stride, ~qbit);
+            const Ring cf = C.cont(1), sf = C.stop(1);
+            atomicAnd(cf.m + (size_t)(q >> 6) * cf.stride, ~qbit);                // edge q -> q+1
+            atomicAnd(sf.m + (size_t)(q >> 6) * sf.stride, ~qbit);
+            const u64 qpbit = 1ull << (qp & 63);
+            atomicAnd(cf.m + (size_t)(qp >> 6) * cf.stride, ~qpbit);              // edge q-1 -> q
+            atomicAnd(sf.m + (size_t)(qp >> 6) * sf.stride, ~qpbit);
+        }
+        {   // bookkeeping mirrored on every lane of the group
+            const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+            const unsigned stop_b = (__ballot_sync(0xffffffffu, stopped) >> lane0) & gmask;
+            const unsigned spawn_b = (__ballot_sync(0xffffffffu, spawn) >> lane0) & gmask;
+            const unsigned zero_b = (__ballot_sync(0xffffffffu, has && res.kind == EV_ZERO) >> lane0) & gmask;
+            int st = 0;
+            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew + __popc(spawn_b & ((1u << g) - 1u)), st);
+            const unsigned ovf_b = (__ballot_sync(0xffffffffu, st != 0) >> lane0) & gmask;
+            nlive -= __popc(stop_b);
+            nnew += __popc(spawn_b);
+            if (zero_b) status |= STO_CAND_ZERO_SPEED;
+            if (ovf_b) status |= STO_CAND_ROW_OVERFLOW;
+        }
+        __syncwarp();
+        L = live.word(w);
 #else
         // host emulation of the G lanes: all evaluations first (frozen state), then the commits in row order
         EvalRes res[G];
