@@ -610,6 +610,159 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
     return w;
 }
 
+// ---- lane groups on the re-spawned lists ---------------------------------------------------------------------------
+// Up to G fronts of a list that need an evaluation are collected, evaluated at once (one per lane, state as it stood)
+// and committed together.  The list is in creation order, positions are arbitrary, so a batch must stop before a front
+// whose classification or inputs an uncommitted member could change: backward, the front one sample BELOW a member
+// (the member writes its source sample); forward, a front on the SAME sample or the one ABOVE (same target / the
+// member writes its source).  Fronts are kept in place while pending (their list slot is reserved) and a front that
+// turns out to stop leaves a tombstone (-1) that the next walk drops.
+template <bool FWD, int G>
+STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                                   int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
+                                   int& status, int g, int lane0) {
+    const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
+    const Ring cont = C.cont(d), stop = C.stop(d);
+    int32_t* list = FWD ? W.spF : W.spB;
+    (void)g; (void)lane0;
+    if (skip) nlist = 0;
+    int r = 0, w = 0, held = -2;  // held: an entry read but not yet classified (-2 = none)
+#if defined(__CUDA_ARCH__)
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(C.ring);
+#pragma unroll 1
+    for (int k = 0; k < STO_LIST_RING; ++k) {
+        if (k < nlist)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)(k * C.ring_stride)),
+                         "l"(list + at(k, ld, b)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
+    for (;;) {
+        int cnt = 0;
+        int pend_p[G], pend_slot[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) { pend_p[k] = -1; pend_slot[k] = -1; }
+        while (cnt < G && (held != -2 || r < nlist)) {
+            int iv;
+            if (held != -2) { iv = held; held = -2; }
+            else {
+#if defined(__CUDA_ARCH__)
+                asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");
+                const int slot = (r & (STO_LIST_RING - 1)) * C.ring_stride;
+                iv = C.ring[slot];
+                if (r + STO_LIST_RING < nlist)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
+                                 "l"(list + at(r + STO_LIST_RING, ld, b)) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+                iv = list[at(r, ld, b)];
+#endif
+                ++r;
+                if (iv < 0) continue;  // tombstone of an earlier walk
+            }
+            int p = FWD ? iv + s : iv - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            bool conflict = false;
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (k < cnt) {
+                    const int pa = pend_p[k];
+                    if (FWD) { const int pa1 = (pa + 1 == N) ? 0 : pa + 1; conflict = conflict || p == pa || p == pa1; }
+                    else { const int pam = (pa == 0) ? N - 1 : pa - 1; conflict = conflict || p == pam; }
+                }
+            }
+            if (conflict) { held = iv; break; }
+            ++steps;
+            if (cont.test(p)) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; continue; }
+            if (stop.test(p)) continue;  // the front stops here: dropped from the list
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+                if (k == cnt) { pend_p[k] = p; pend_slot[k] = w; }
+            if (w != r - 1) list[at(w, ld, b)] = iv;   // slot reserved; a tombstone replaces it if the front stops
+            ++w;
+            ++cnt;
+        }
+        if (!warp_any(cnt > 0)) break;
+#if defined(__CUDA_ARCH__)
+        int p = -1, slot = -1;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+            if (k == g) { p = pend_p[k]; slot = pend_slot[k]; }
+        const bool has = g < cnt;
+        const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+        EvalRes res;
+        res.kind = EV_NONE; res.v_new = 0.0; res.a_new = 0.0;
+        if (has) res = eval_pure(A, V, b, FWD, p, q, lat0);
+        __syncwarp();
+        const bool stopped = has && (res.kind == EV_STOP || res.kind == EV_SPAWN || res.kind == EV_RESPAWN ||
+                                     res.kind == EV_ZERO);
+        const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
+        const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
+        if (has) {
+            const u64 pbit = 1ull << (p & 63);
+            u64* const contw = cont.m + (size_t)(p >> 6) * cont.stride;
+            u64* const stopw = stop.m + (size_t)(p >> 6) * stop.stride;
+            if (changed) {
+                double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
+                rq[0] = res.v_new;
+                rq[1] = res.a_new;
+            }
+            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atomicOr(contw, pbit); atomicAnd(stopw, ~pbit); }
+            else if (res.kind == EV_STOP) { atomicOr(stopw, pbit); atomicAnd(contw, ~pbit); }
+            else if (res.kind == EV_SPAWN) { atomicAnd(contw, ~pbit); atomicAnd(stopw, ~pbit); }
+            if (stopped) list[at(slot, ld, b)] = -1;
+        }
+        __syncwarp();
+        if (changed) {   // memo_invalidate(q) minus this front's own edge (bit p of its own direction's planes)
+            const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
+            const Ring cb = C.cont(0), sb = C.stop(0), cf = C.cont(1), sf = C.stop(1);
+            const u64 qbit = 1ull << (q & 63), qnbit = 1ull << (qn & 63), qpbit = 1ull << (qp & 63);
+            atomicAnd(cb.m + (size_t)(q >> 6) * cb.stride, ~qbit);                    // edge q -> q-1
+            atomicAnd(sb.m + (size_t)(q >> 6) * sb.stride, ~qbit);
+            atomicAnd(cf.m + (size_t)(q >> 6) * cf.stride, ~qbit);                    // edge q -> q+1
+            atomicAnd(sf.m + (size_t)(q >> 6) * sf.stride, ~qbit);
+            if (FWD) {   // own edge is p -> q = (q-1 -> q): skip it, clear q+1 -> q
+                atomicAnd(cb.m + (size_t)(qn >> 6) * cb.stride, ~qnbit);
+                atomicAnd(sb.m + (size_t)(qn >> 6) * sb.stride, ~qnbit);
+            } else {     // own edge is p -> q = (q+1 -> q): skip it, clear q-1 -> q
+                atomicAnd(cf.m + (size_t)(qp >> 6) * cf.stride, ~qpbit);
+                atomicAnd(sf.m + (size_t)(qp >> 6) * sf.stride, ~qpbit);
+            }
+        }
+        {
+            const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+            const unsigned spawn_b = (__ballot_sync(0xffffffffu, spawn) >> lane0) & gmask;
+            const unsigned zero_b = (__ballot_sync(0xffffffffu, has && res.kind == EV_ZERO) >> lane0) & gmask;
+            int st = 0;
+            if (spawn) memo_spawn(A, W, b, q, s, nB, nnew + __popc(spawn_b & ((1u << g) - 1u)), st);
+            const unsigned ovf_b = (__ballot_sync(0xffffffffu, st != 0) >> lane0) & gmask;
+            nnew += __popc(spawn_b);
+            if (zero_b) status |= STO_CAND_ZERO_SPEED;
+            if (ovf_b) status |= STO_CAND_ROW_OVERFLOW;
+        }
+        __syncwarp();
+#else
+        // host emulation: evaluate every member against the state as it stands, then commit in list order
+        EvalRes res[G];
+        int qq[G];
+        for (int k = 0; k < cnt; ++k) {
+            const int p = pend_p[k];
+            qq[k] = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+            res[k] = eval_pure(A, V, b, FWD, p, qq[k], lat0);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            bool spawn, changed;
+            const bool stopped = apply_res(A, C, b, FWD, pend_p[k], qq[k], res[k], status, spawn, changed);
+            if (spawn) { memo_spawn(A, W, b, qq[k], s, nB, nnew, status); ++nnew; }
+            if (stopped) list[at(pend_slot[k], ld, b)] = -1;
+        }
+#endif
+        if (status != 0) { nlist = r; held = -2; }   // abandon the walk of a failed candidate
+    }
+    return w;
+}
+
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
 template <int G>
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
@@ -666,7 +819,9 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         else
             memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
         STO_CLK(1)
-        const int wB = memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
+        const int wB = (G > 1)
+            ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0)
+            : memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
@@ -676,7 +831,9 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         int wF;
         {
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
-            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
+            wF = (G > 1)
+                ? memo_spawned_rows_group<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
+                : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
         }
         STO_CLK(4)
         if (!done) {
