@@ -684,6 +684,9 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
             ++cnt;
         }
         if (!warp_any(cnt > 0)) break;
+#if defined(STO_HOSTSIM_COUNTERS)
+        g_sp_evals[d] += cnt; ++g_sp_changed[d];   // (re-used here: evaluations / batches of the group walker)
+#endif
 #if defined(__CUDA_ARCH__)
         int p = -1, slot = -1;
 #pragma unroll
@@ -831,9 +834,15 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         int wF;
         {
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
+#if defined(STO_GROUP_SF)
             wF = (G > 1)
                 ? memo_spawned_rows_group<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
+#else
+            // forward re-spawned fronts mostly conflict with their list neighbours (1.6 per batch measured): the
+            // one-at-a-time walker is cheaper there
+            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
+#endif
         }
         STO_CLK(4)
         if (!done) {
