@@ -244,9 +244,12 @@ def run_gpu_arm(args):
         ev.lap_times_host_into(pinned[j & 1].data_ptr(), B, lap_pin.data_ptr(), st_pin.data_ptr())
     barrier()
     t0 = time.perf_counter()
+    e2e_calls = []
     for j in range(args.steps):
+        tc = time.perf_counter()
         ev.lap_times_host_into(pinned[j & 1].data_ptr(), B, lap_pin.data_ptr(), st_pin.data_ptr())
         _ = float(lap_pin.min())    # the step's result is consumed on the host
+        e2e_calls.append(1e3 * (time.perf_counter() - tc))
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -304,7 +307,8 @@ def run_gpu_arm(args):
                        "parallelism": f"candidate-sharded x{world}; all-gather of (lap, index) + argmin"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * M * B),
                     "d2h_bytes_per_step": int(12 * B),
-                    "api": "sto_lap_time_host_f64 (pinned host offsets [B][M] in, lap/status out)"},
+                    "api": "sto_lap_time_host_f64 (pinned host offsets [B][M] in, lap/status out)",
+                    "ms_per_call": [round(x, 2) for x in e2e_calls]},
             "gpu_launches": int(5 * args.steps),
             "kernels_per_step": ["zero_status_kernel", "fit_kernel", "eval_kernel",
                                  "qss_memo_kernel" if args.qss == "memo" else "qss_plain_kernel", "argmin_kernel"],
