@@ -571,43 +571,16 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
         bool pending = false;
         while (r < nlist) {
 #if defined(__CUDA_ARCH__)
-            // The next (up to) four unread entries and their memo words are fetched together - independent shared
-            // memory loads instead of a dependent chain per front - and then consumed in list order up to the first
-            // front that needs an evaluation.  Nothing inside a chunk changes a memo before that point.
-            asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 4) : "memory");
-            int civ[4], cpp[4];
-            u64 ccw[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                civ[k] = (r + k < nlist) ? C.ring[((r + k) & (STO_LIST_RING - 1)) * C.ring_stride] : -1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int pk = FWD ? civ[k] + s : civ[k] - s;
-                if (pk >= N) pk -= N;
-                if (pk < 0) pk += N;
-                cpp[k] = pk;
-                ccw[k] = (civ[k] >= 0) ? cont.word(pk >> 6) : 0ull;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (pending || civ[k] < 0) continue;
-                const int slot = (r & (STO_LIST_RING - 1)) * C.ring_stride;   // consume entry r, refill its ring slot
-                if (r + STO_LIST_RING < nlist)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
-                                 "l"(list + at(r + STO_LIST_RING, ld, b)) : "memory");
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                ++r;
-                ++steps;
-                iv = civ[k];
-                p = cpp[k];
-                if ((ccw[k] >> (p & 63)) & 1ull) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; continue; }
-                if (stop.test(p)) continue;  // the front stops here: dropped from the list
-                q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
-                pending = true;
-            }
-            if (pending) break;
+            asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");
+            const int slot = (r & (STO_LIST_RING - 1)) * C.ring_stride;
+            iv = C.ring[slot];
+            if (r + STO_LIST_RING < nlist)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
+                             "l"(list + at(r + STO_LIST_RING, ld, b)) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
 #else
             iv = list[at(r, ld, b)];
+#endif
             ++r;
             ++steps;
             p = FWD ? iv + s : iv - s;
@@ -618,7 +591,6 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
             pending = true;
             break;
-#endif
         }
         STO_SUBCLK(2)
         if (!warp_any(pending)) break;
