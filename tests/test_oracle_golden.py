@@ -94,3 +94,17 @@ def test_lap_batch_threads_agree():
     l4, s4 = O.lap_batch(d["centre_x"], d["centre_y"], nx, ny, d["offsets"], d["ts"], np.zeros(len(d["ts"])), veh, 4, 1)
     assert np.array_equal(l1, l4) and not s1.any() and not s4.any()
     assert np.max(np.abs(l1 - d["ref_lap"])) < 1e-6
+
+
+def test_vehicle_mirror_matches_reference_lookups():
+    """Host Vehicle mirror: acc/dcc table look-ups and the friction-ellipse coupling, bit for bit against values the
+    reference's Vehicle produced (models/vehicle.py:26-47), for the 5-row-table vehicle."""
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle, VehicleParams
+    d = golden("sim_s10k3_i10_vehicle5")
+    v = Vehicle(VehicleParams(d["veh_acc_lookup"], d["veh_dcc_lookup"], *d["veh_scalars"]))
+    assert np.array_equal(v.acc_intp.c, d["veh_acc_c"]) and np.array_equal(v.dcc_intp.x, d["veh_dcc_x"])
+    assert np.array_equal([float(v.lookup_acc_from_speed(g)) for g in d["ppoly_grid"]], d["ppoly_acc"])
+    assert np.array_equal([float(v.lookup_dcc_from_speed(g)) for g in d["ppoly_grid"]], d["ppoly_dcc"])
+    assert np.array_equal([float(v.lookup_acc_circle(lon=l)[0]) for l in d["ellipse_lon"]], d["ellipse_lat"])
+    pos, neg = v.lookup_acc_circle(lat=3.0)
+    assert pos > 0 > neg
