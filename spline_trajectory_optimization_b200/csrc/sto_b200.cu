@@ -321,6 +321,19 @@ __global__ void qss_memo_gplanes_kernel(sto::QssArgs A, sto::MemoWork W, int lan
     sto::qss_memo_candidate<1>(A, W, C, V, b, active, 0, lane);
 }
 
+// Large-batch variant 2: the two CONT planes in shared memory (736 B per Monza candidate -> every warp of a 32 k batch
+// stays resident), live / STOP planes in global memory.
+__global__ void qss_memo_mixed_kernel(sto::QssArgs A, sto::MemoWork W, int lanes,
+                                      const __grid_constant__ sto_vehicle_f64 V) {
+    bool active;
+    const int b = candidate_of_thread(lanes, A.B, active);
+    const int lane = threadIdx.x & 31;
+    int32_t* ring = reinterpret_cast<int32_t*>(sto_planes + (size_t)2 * W.W * 32);
+    const sto::MemoCtx C = sto::memo_bind_mixed(W.gplanes + (size_t)b * 6 * W.W, sto_planes, 32, lane, ring, 32, lane,
+                                                A.N, W.W);
+    sto::qss_memo_candidate<1>(A, W, C, V, b, active, 0, lane);
+}
+
 // Candidates per warp for the QSS kernels: aim for a few warps on each of the 148 SMs before filling warps.
 int pick_lanes(int B, size_t smem_per_candidate) {
     int lanes = 32;
@@ -355,7 +368,15 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         if (global_planes) {
             const int lanes = pick_lanes(A.B, 0);
             const int warps = (A.B + lanes - 1) / lanes;
-            qss_memo_gplanes_kernel<<<warps, 32, 0, st>>>(A, w.memo, lanes, *vehicle);
+            const size_t mixed_smem = (size_t)2 * w.memo.W * 32 * sizeof(unsigned long long) + STO_LIST_RING * 32 * sizeof(int32_t);
+            const bool mixed = (pl && pl[0] == 'g') ? (pl[1] != '0') : true;   // "g0" forces the all-global variant
+            if (mixed && mixed_smem <= kMemoSmemBudget / 4) {
+                STO_CUDA(cudaFuncSetAttribute(qss_memo_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)mixed_smem));
+                qss_memo_mixed_kernel<<<warps, 32, mixed_smem, st>>>(A, w.memo, lanes, *vehicle);
+            } else {
+                qss_memo_gplanes_kernel<<<warps, 32, 0, st>>>(A, w.memo, lanes, *vehicle);
+            }
             STO_CUDA(cudaGetLastError());
             return STO_OK;
         }

@@ -113,15 +113,19 @@ struct Ring {
 
 // The six planes of one candidate: plane k, word w at base[(k * W + w) * stride] (base already offset by the lane).
 // Rings are formed on the fly from (kind, direction) so that nothing is indexed dynamically out of registers.
+// Each kind of plane (live / CONT / STOP; two directions each) has its own base and stride, so the kinds can live in
+// different memories: all in shared memory (small batches), all in global memory, or the hot CONT planes in shared
+// memory and the rest in global (large batches).
 struct MemoCtx {
-    u64* base;
-    int stride, N, W;
+    u64 *live_base, *cont_base, *stop_base;   // [2 directions][W words] each, word w of direction d at base[(d*W + w)*stride]
+    int live_stride, cont_stride, stop_stride;
+    int N, W;
     int32_t* ring;  // shared-memory prefetch ring of this lane for the re-spawned lists: slot k at ring[k * ring_stride]
     int ring_stride;
-    STO_HD Ring plane(int k) const { return Ring{base + (size_t)k * W * stride, stride, N, W}; }
-    STO_HD Ring live(int d) const { return plane(0 + d); }   // d = 0 backward (edge p -> p-1), 1 forward (p -> p+1)
-    STO_HD Ring cont(int d) const { return plane(2 + d); }
-    STO_HD Ring stop(int d) const { return plane(4 + d); }
+    // d = 0 backward (edge p -> p-1), 1 forward (p -> p+1)
+    STO_HD Ring live(int d) const { return Ring{live_base + (size_t)d * W * live_stride, live_stride, N, W}; }
+    STO_HD Ring cont(int d) const { return Ring{cont_base + (size_t)d * W * cont_stride, cont_stride, N, W}; }
+    STO_HD Ring stop(int d) const { return Ring{stop_base + (size_t)d * W * stop_stride, stop_stride, N, W}; }
 };
 
 #ifndef STO_LIST_RING
@@ -130,13 +134,22 @@ struct MemoCtx {
 
 // Planes in global memory (candidate-major, stride 1), prefetch ring in shared memory ([STO_LIST_RING][ring_stride]).
 STO_HD MemoCtx memo_bind_global(u64* planes, int32_t* ring, int ring_stride, int lane, int N, int W) {
-    return MemoCtx{planes, 1, N, W, ring + lane, ring_stride};
+    return MemoCtx{planes, planes + 2 * (size_t)W, planes + 4 * (size_t)W, 1, 1, 1, N, W, ring + lane, ring_stride};
+}
+
+// Large batches: CONT planes (read by every search step) in shared memory [2][W][cont_stride], column `col`; live and
+// STOP planes candidate-major in global memory (`planes`: [live B, live F, stop B, stop F] x W words).
+STO_HD MemoCtx memo_bind_mixed(u64* planes, u64* cont_smem, int cont_stride, int col, int32_t* ring, int ring_stride,
+                               int lane, int N, int W) {
+    return MemoCtx{planes, cont_smem + col, planes + 2 * (size_t)W, 1, cont_stride, 1, N, W, ring + lane, ring_stride};
 }
 
 // Planes in shared memory: [6 planes][W words][stride candidates] u64, this candidate in column `col`; the prefetch
 // ring ([STO_LIST_RING][ring_stride] int32) is per LANE (the lanes of a group walk the lists redundantly).
 STO_HD MemoCtx memo_bind(u64* planes, int stride, int col, int32_t* ring, int ring_stride, int lane, int N, int W) {
-    return MemoCtx{planes + col, stride, N, W, ring + lane, ring_stride};
+    u64* base = planes + col;
+    return MemoCtx{base, base + 2 * (size_t)W * stride, base + 4 * (size_t)W * stride, stride, stride, stride, N, W,
+                   ring + lane, ring_stride};
 }
 
 // Shared memory of one warp hosting `cands` candidates.
