@@ -188,6 +188,9 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...", printed on stdout when the
+        # image exports NCCL_DEBUG=VERSION/INFO) out of it unless explicitly asked for
+        os.environ["NCCL_DEBUG"] = os.environ.get("STO_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 

@@ -14,11 +14,12 @@ numbers, argument meaning and quirks.  Differences are behind the API:
 import copy
 import ctypes as C
 import pickle
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
 from scipy import interpolate
-from scipy.integrate import quad
+from scipy.integrate import IntegrationWarning, quad
 from scipy.interpolate import BSpline
 
 
@@ -272,7 +273,11 @@ class BSplineTrajectory:
         return np.sqrt(interpolate.splev(t, self._spl_x, der=1) ** 2 + interpolate.splev(t, self._spl_y, der=1) ** 2)
 
     def _section_length(self, t_min, t_max):
-        length, _ = quad(self._speed, t_min, t_max, limit=1000)
+        # same call as the reference (models/trajectory.py:228-230); its whole-lap integral always trips QUADPACK's
+        # round-off IntegrationWarning, which is noise here
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", IntegrationWarning)
+            length, _ = quad(self._speed, t_min, t_max, limit=1000)
         return length
 
     def eval_sectional_length(self, ts):
