@@ -190,7 +190,10 @@ def run_gpu_arm(args):
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...", printed on stdout when the
         # image exports NCCL_DEBUG=VERSION/INFO) out of it unless explicitly asked for
-        os.environ["NCCL_DEBUG"] = os.environ.get("STO_NCCL_DEBUG", "WARN")
+        if "STO_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["STO_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)   # even WARN prints the version banner
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
