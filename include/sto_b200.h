@@ -99,6 +99,14 @@ int sto_release(void);                /* frees the device arena cached by the *_
  * `work` needs sto_fit_workspace_bytes(M, B) bytes.
  */
 size_t sto_fit_workspace_bytes(int M, int B);
+/* Solver of the cyclic tridiagonal collocation system.  Default (mode -1 or 1): a group of up to 32 lanes shares each
+ * candidate - block elimination per lane with the interface unknowns kept symbolic, the interface system by parallel
+ * cyclic reduction over __shfl_sync, one division per row; the lane count follows the batch size (32 for a few long
+ * lines, 1 for batches that fill the GPU on their own).  mode 0: one-lane Thomas + Sherman-Morrison recurrences, the
+ * solver oracle/sto_oracle.c restates (bit-identical to it).  Same knots either way; coefficients agree to ~1e-15
+ * relative, both within 3e-14 of FITPACK on the golden lines. */
+void sto_set_fit_partition(int mode);
+int sto_fit_partition_lanes(int M, int B);   /* lanes per candidate of the partitioned solve; 0 = Thomas solver selected */
 int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, const double* normal_x,
                                const double* normal_y, const double* offsets, const double* px,
                                const double* py, int M, int B, int ld, double* u, double* cx, double* cy,

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "sto_lap_time_host_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [C.POINTER(StoVehicle), C.c_int, _vp, _vp,
                                         C.c_int, C.c_size_t]),
     "sto_set_stage_timing": (C.c_int, [C.c_int]),
+    "sto_set_fit_partition": (None, [C.c_int]),
+    "sto_fit_partition_lanes": (C.c_int, [C.c_int, C.c_int]),
     "sto_last_stage_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "sto_argmin_f64": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "sto_transpose_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),

@@ -55,6 +55,29 @@ int pick_fit_split(int B) {
     if (B <= 65536) return 2;
     return 1;
 }
+// The cyclic solve of the fit: by default a group of lanes shares each candidate (sto_fit.cuh, "partitioned cyclic
+// solve": block elimination per lane + PCR over warp shuffles, one division per row); mode 0 selects the one-lane
+// Thomas + Sherman-Morrison recurrences (bit-identical to oracle/sto_oracle.c's solver).  g_fit_part: -1 / 1 partitioned,
+// 0 Thomas.  Lanes per candidate measured on B200 (tools/fit_part_bench.py, ms at M = 2895 | 23,160):
+//   B =   256: Thomas x8 2.7 | 30.7   partitioned x32 0.27 |  2.7
+//   B =  1024: Thomas x8 3.6 | 32.8   partitioned x16 0.64 |  7.7   (x32 0.58 | 11.3)
+//   B =  4096: Thomas x8 4.2 | 34.3   partitioned x8  1.81 | 16.1
+//   B = 16384: Thomas x1 8.8 | 71.2   partitioned x4  3.60 | 29.8
+int g_fit_part = -1;
+struct FitPlan { int split; bool part; };
+FitPlan pick_fit_plan(int M, int B) {
+    int mode = g_fit_part;
+    if (const char* e = getenv("STO_FIT_PART")) mode = atoi(e);
+    if (mode == 0) return FitPlan{pick_fit_split(B), false};
+    int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 32768) ? 4 : (B <= 131072) ? 2 : 1;
+    if (const char* e = getenv("STO_FIT_SPLIT")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
+    }
+    if (M < 256) lanes = 1;   // one block (sto::fit_part_blocks): nothing to share
+    return FitPlan{lanes, true};
+}
+
 // Lanes per candidate for kernels whose samples are independent: fill ~8 warps per SM before going one-per-candidate.
 int pick_split(int B, int N) {
     int split = 1;
@@ -130,11 +153,29 @@ QssWork carve_qss(Carver& c, int N, size_t ld, int impl, bool need_chords, bool 
 // ---- kernels ---------------------------------------------------------------------------------------------
 // `split` (a power of two <= 32) lanes share a candidate: per-row work is split over them and the three Thomas
 // recurrences run side by side (sto_fit.cuh).  Whole warps stay alive so the group syncs are warp-uniform.
+// PART_E > 0: the `split` lanes solve the cyclic system together (partitioned elimination + PCR over warp shuffles),
+// PART_E blocks per lane; PART_E = 0: Thomas recurrences.
+template <int PART_E>
 __global__ void fit_kernel(sto::FitArgs A, int split) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = t / split, g = t % split;
     const int lane0 = (threadIdx.x & 31) & ~(split - 1);
-    sto::fit_candidate_lane(A, b < A.B ? b : A.B - 1, b < A.B, g, split, lane0);
+    sto::fit_candidate_lane<PART_E>(A, b < A.B ? b : A.B - 1, b < A.B, g, split, lane0);
+}
+
+void launch_fit(const sto::FitArgs& A, const FitPlan& plan, cudaStream_t st) {
+    const int split = plan.split;
+    const int block = pick_block(A.B * split);
+    const int grid = grid_for(A.B * split, block);
+    if (!plan.part) { fit_kernel<0><<<grid, block, 0, st>>>(A, split); return; }
+    switch (32 / split) {   // blocks per lane (one block in all when M < 256: plan.split == 1, any instantiation)
+        case 1: fit_kernel<1><<<grid, block, 0, st>>>(A, split); break;
+        case 2: fit_kernel<2><<<grid, block, 0, st>>>(A, split); break;
+        case 4: fit_kernel<4><<<grid, block, 0, st>>>(A, split); break;
+        case 8: fit_kernel<8><<<grid, block, 0, st>>>(A, split); break;
+        case 16: fit_kernel<16><<<grid, block, 0, st>>>(A, split); break;
+        default: fit_kernel<32><<<grid, block, 0, st>>>(A, split); break;
+    }
 }
 
 // `split` lanes share a candidate, each taking a contiguous slice of its samples (samples are independent): small
@@ -389,7 +430,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         int G = 4;
         if (const char* e = getenv("STO_QSS_GROUP")) {
             const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4 || v == 8) G = v;
+            if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) G = v;
         }
         const size_t per_cand = sto::memo_plane_bytes(A.N);
         int cpw = pick_lanes(A.B, per_cand);
@@ -402,7 +443,9 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         qss_memo_kernel<GG><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
     } while (0)
-        if (G == 8) STO_LAUNCH_MEMO(8);
+        if (G == 32) STO_LAUNCH_MEMO(32);
+        else if (G == 16) STO_LAUNCH_MEMO(16);
+        else if (G == 8) STO_LAUNCH_MEMO(8);
         else if (G == 4) STO_LAUNCH_MEMO(4);
         else if (G == 2) STO_LAUNCH_MEMO(2);
         else STO_LAUNCH_MEMO(1);
@@ -419,6 +462,13 @@ extern "C" {
 
 int sto_abi_version(void) { return STO_B200_ABI_VERSION; }
 const char* sto_last_error(void) { return g_err.c_str(); }
+
+void sto_set_fit_partition(int mode) { g_fit_part = (mode < 0) ? -1 : (mode > 0 ? 1 : 0); }
+int sto_fit_partition_lanes(int M, int B) {
+    if (M < 3 || B < 1) return 0;
+    const FitPlan p = pick_fit_plan(M, B);
+    return p.part ? p.split : 0;
+}
 
 int sto_device_count(void) {
     int n = 0;
@@ -461,9 +511,7 @@ int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, c
     A.cenx = centre_x; A.ceny = centre_y; A.nrmx = normal_x; A.nrmy = normal_y; A.off = offsets;
     A.px = px; A.py = py; A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int split = pick_fit_split(B);
-    const int block = pick_block(B * split);
-    fit_kernel<<<grid_for(B * split, block), block, 0, st>>>(A, split);
+    launch_fit(A, pick_fit_plan(M, B), st);
     STO_CUDA(cudaGetLastError());
     return STO_OK;
 }
@@ -623,9 +671,7 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     F.M = M; F.B = B; F.ld = ld; F.u = w.u; F.cx = w.cx; F.cy = w.cy; F.status = status;
     F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz;
     {
-        const int split = pick_fit_split(B);
-        const int fblock = pick_block(B * split);
-        fit_kernel<<<grid_for(B * split, fblock), fblock, 0, st>>>(F, split);
+        launch_fit(F, pick_fit_plan(M, B), st);
     }
     STO_CUDA(cudaGetLastError());
     stage_mark(2, st);

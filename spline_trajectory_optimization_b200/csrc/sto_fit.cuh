@@ -105,19 +105,68 @@ STO_HD double fit_phase_cumsum(const FitArgs& A, int b) {
     return acc;
 }
 
+#if defined(__CUDA_ARCH__)
+// phase B for a group of G lanes: the additions stay one chain in row order (u is bit-identical to the one-lane sum and
+// to FITPACK's), but the loads and stores are spread over the lanes: lane g fetches row c0 + g of every chunk of G
+// rows, the values travel by __shfl_sync, every lane carries the same running sum and keeps the prefix of its own row.
+// The chain is then bound by the DADD latency instead of a global round trip per STO_FIT_CHUNK rows.
+STO_D double fit_phase_cumsum_group(const FitArgs& A, int b, bool active, int g, int G, int lane0) {
+    const int M = A.M, ld = A.ld;
+    double acc = 0.0;
+    if (active && g == 0) A.u[at(0, ld, b)] = 0.0;
+    double vn = (active && 1 + g <= M) ? A.u[at(1 + g, ld, b)] : 0.0;
+    for (int c0 = 1; c0 <= M; c0 += G) {
+        const double v = vn;
+        const int i2 = c0 + G + g;
+        vn = (active && i2 <= M) ? A.u[at(i2, ld, b)] : 0.0;
+        double mine = 0.0;
+        for (int k = 0; k < G; ++k) {
+            acc = acc + __shfl_sync(0xffffffffu, v, lane0 + k);   // rows past M contribute + 0.0 (exact)
+            if (k == g) mine = acc;
+        }
+        if (active && c0 + g <= M) A.u[at(c0 + g, ld, b)] = mine;
+    }
+    return acc;
+}
+#endif
+
 // phase C: normalise (rows split over lanes); phase D: collocation coefficients b0 -> cx[j], b2 -> cy[j] (scratch use)
 STO_HD void fit_phase_normalise(const FitArgs& A, int b, int g, int G, double total) {
     const int M = A.M, ld = A.ld;
-    for (int i = 1 + g; i < M; i += G) A.u[at(i, ld, b)] = A.u[at(i, ld, b)] / total;
+    const int per = (M - 1 + G - 1) / G;                       // rows 1 .. M-1 in contiguous blocks, chunked loads
+    const int i0 = 1 + g * per, i1 = (i0 + per < M) ? i0 + per : M;
+    for (int c0 = i0; c0 < i1; c0 += STO_FIT_CHUNK) {
+        double us[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) us[k] = (c0 + k < i1) ? A.u[at(c0 + k, ld, b)] : 1.0;
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k)
+            if (c0 + k < i1) A.u[at(c0 + k, ld, b)] = us[k] / total;
+    }
     if (g == 0) A.u[at(M, ld, b)] = 1.0;
 }
 STO_HD void fit_phase_rows(const FitArgs& A, int b, int g, int G) {
+    // every lane takes a contiguous block of rows and slides a five-knot window along it: one new knot per row,
+    // fetched STO_FIT_CHUNK rows ahead (the value of each row is a pure function of its knots: any split is bit-identical)
     const int M = A.M, ld = A.ld;
-    for (int j = g; j < M; j += G) {
-        const double t0 = fit_knot(A, j - 2, b), t1 = fit_knot(A, j - 1, b), t2 = fit_knot(A, j, b),
-                     t3 = fit_knot(A, j + 1, b), t4 = fit_knot(A, j + 2, b);
-        A.cx[at(j, ld, b)] = ((t3 - t2) * (t3 - t2)) / ((t3 - t0) * (t3 - t1));
-        A.cy[at(j, ld, b)] = ((t2 - t1) * (t2 - t1)) / ((t4 - t1) * (t3 - t1));
+    const int per = (M + G - 1) / G;
+    const int j0 = g * per, j1 = (j0 + per < M) ? j0 + per : M;
+    if (j0 >= j1) return;
+    double t0 = fit_knot(A, j0 - 2, b), t1 = fit_knot(A, j0 - 1, b), t2 = fit_knot(A, j0, b), t3 = fit_knot(A, j0 + 1, b);
+    for (int c0 = j0; c0 < j1; c0 += STO_FIT_CHUNK) {
+        double nk[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) nk[k] = (c0 + k < j1) ? fit_knot(A, c0 + k + 2, b) : 0.0;
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = c0 + k;
+            if (j < j1) {
+                const double t4 = nk[k];
+                A.cx[at(j, ld, b)] = ((t3 - t2) * (t3 - t2)) / ((t3 - t0) * (t3 - t1));
+                A.cy[at(j, ld, b)] = ((t2 - t1) * (t2 - t1)) / ((t4 - t1) * (t3 - t1));
+                t0 = t1; t1 = t2; t2 = t3; t3 = t4;
+            }
+        }
     }
 }
 
@@ -302,6 +351,315 @@ STO_HD void fit_phase_coefficients(const FitArgs& A, int b, int g, int G, double
     }
 }
 
+// ---- partitioned cyclic solve: a GROUP of P lanes per candidate (long, finely sampled tracks) ------------------------
+// The Thomas recurrences above are one dependent chain of M divisions per candidate; at M ~ 23 k (0.25 m sampling)
+// that chain, not the batch, bounds the fit.  Here the M rows are cut into P contiguous blocks, one per lane:
+//   1. every lane eliminates the interior of its block (rows s .. e-2) with the two neighbouring interface unknowns
+//      X_{k-1} = e_{s-1} and X_k = e_{e-1} kept symbolic:  e_j + cp_j e_{j+1} = z_j - zl_j X_{k-1};
+//   2. a backward recurrence gives the block's first unknown as e_s = y - wl X_{k-1} - wr X_k;
+//   3. row e-1 of every block, with e_{e-2} from (1) and e_e from the NEXT lane's (2) (one __shfl_sync), is a cyclic
+//      tridiagonal equation in (X_{k-1}, X_k, X_{k+1}): P equations, solved across the lanes by parallel cyclic
+//      reduction on warp shuffles (log2 P - 1 steps and a final 2 x 2 solve; the period is handled by the ring of
+//      lanes itself, no Sherman-Morrison correction);
+//   4. every lane back-substitutes its block and writes the coefficients (e -> c rotation and wrap as above).
+// Critical path: 3 sweeps over M / P rows + log2 P shuffle rounds instead of 2 sweeps over M rows.  The arithmetic
+// differs from the one-lane Thomas solve in rounding only (coefficients agree to ~1e-15 relative; tests/).
+struct PartFwd { double cp, zx, zy, zl; };     // forward-eliminated row e-2 of a block
+struct PartFirst { double yx, yy, wl, wr; };   // first unknown of a block: e_s = y - wl X_{k-1} - wr X_k
+struct PartEq { double a, d, c, rx, ry; };     // a X_{k-h} + d X_k + c X_{k+h} = r
+
+STO_HD int fit_part_begin(int M, int k, int P) { return (int)(((long long)k * M) / P); }   // balanced blocks, >= M/P rows
+
+STO_HD PartFwd fit_part_forward(const FitArgs& A, int b, int s, int e) {
+    const int ld = A.ld;
+    double cpp = 0.0, zxp = 0.0, zyp = 0.0, zlp = 0.0;
+    for (int j0 = s; j0 < e - 1; j0 += STO_FIT_CHUNK) {
+        double b0s[STO_FIT_CHUNK], b2s[STO_FIT_CHUNK], pxs[STO_FIT_CHUNK], pys[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            b0s[k] = b2s[k] = pxs[k] = pys[k] = 0.0;
+            if (j < e - 1) {
+                b0s[k] = A.cx[at(j, ld, b)];
+                b2s[k] = A.cy[at(j, ld, b)];
+                fit_point(A, j, b, pxs[k], pys[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 + k;
+            if (j >= e - 1) break;
+            const double b0 = b0s[k], b2 = b2s[k];
+            const double b1 = (1.0 - b0) - b2;
+            const double inv = 1.0 / (b1 - b0 * cpp);          // one division per row; cpp = 0 on the block's first row
+            const double ncp = b2 * inv;
+            const double nzx = (pxs[k] - b0 * zxp) * inv;
+            const double nzy = (pys[k] - b0 * zyp) * inv;
+            const double nzl = ((j == s) ? b0 : 0.0 - b0 * zlp) * inv;   // coupling to X_{k-1} enters on the first row only
+            A.cp[at(j, ld, b)] = ncp;
+            A.zx[at(j, ld, b)] = nzx;
+            A.zy[at(j, ld, b)] = nzy;
+            A.zz[at(j, ld, b)] = nzl;
+            cpp = ncp; zxp = nzx; zyp = nzy; zlp = nzl;
+        }
+    }
+    return PartFwd{cpp, zxp, zyp, zlp};
+}
+
+STO_HD PartFirst fit_part_first(const FitArgs& A, int b, int s, int e, const PartFwd& last) {
+    const int ld = A.ld;
+    double yx = last.zx, yy = last.zy, wl = last.zl, wr = last.cp;
+    for (int j0 = e - 3; j0 >= s; j0 -= STO_FIT_CHUNK) {
+        double cs[STO_FIT_CHUNK], xs[STO_FIT_CHUNK], ys[STO_FIT_CHUNK], ls[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            cs[k] = xs[k] = ys[k] = ls[k] = 0.0;
+            if (j >= s) {
+                cs[k] = A.cp[at(j, ld, b)]; xs[k] = A.zx[at(j, ld, b)];
+                ys[k] = A.zy[at(j, ld, b)]; ls[k] = A.zz[at(j, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            if (j0 - k < s) break;
+            yx = xs[k] - cs[k] * yx;
+            yy = ys[k] - cs[k] * yy;
+            wl = ls[k] - cs[k] * wl;
+            wr = 0.0 - cs[k] * wr;
+        }
+    }
+    return PartFirst{yx, yy, wl, wr};
+}
+
+// Row e-1 of a block: b0 e_{e-2} + b1 X_k + b2 e_e = p, with e_{e-2} from this block and e_e from the next one.
+STO_HD PartEq fit_part_equation(const FitArgs& A, int b, int e, const PartFwd& own, const PartFirst& next) {
+    const int i = e - 1;
+    const double b0 = A.cx[at(i, A.ld, b)], b2 = A.cy[at(i, A.ld, b)];
+    const double b1 = (1.0 - b0) - b2;
+    double px, py;
+    fit_point(A, i, b, px, py);
+    PartEq q;
+    q.a = 0.0 - b0 * own.zl;
+    q.d = (b1 - b0 * own.cp) - b2 * next.wl;
+    q.c = 0.0 - b2 * next.wr;
+    q.rx = (px - b0 * own.zx) - b2 * next.yx;
+    q.ry = (py - b0 * own.zy) - b2 * next.yy;
+    return q;
+}
+
+// One step of parallel cyclic reduction: eliminate X_{k-h} and X_{k+h} with the equations of lanes k-h and k+h.
+STO_HD PartEq fit_pcr_combine(const PartEq& me, const PartEq& lo, const PartEq& hi) {
+    const double al = 0.0 - me.a / lo.d, ga = 0.0 - me.c / hi.d;
+    PartEq r;
+    r.a = al * lo.a;
+    r.c = ga * hi.c;
+    r.d = (me.d + al * lo.c) + ga * hi.a;
+    r.rx = (me.rx + al * lo.rx) + ga * hi.rx;
+    r.ry = (me.ry + al * lo.ry) + ga * hi.ry;
+    return r;
+}
+// Last step (h = P/2): lanes k-h and k+h are the same lane `o`; a 2 x 2 system between k and o.
+STO_HD void fit_pcr_final(const PartEq& me, const PartEq& o, double& x, double& y) {
+    const double S = me.a + me.c, So = o.a + o.c;
+    const double det = me.d * o.d - S * So;
+    x = (me.rx * o.d - S * o.rx) / det;
+    y = (me.ry * o.d - S * o.ry) / det;
+}
+STO_HD void fit_pcr_single(const PartEq& me, double& x, double& y) {   // P = 1: X couples to itself on both sides
+    const double d = (me.a + me.d) + me.c;
+    x = me.rx / d;
+    y = me.ry / d;
+}
+
+STO_HD void fit_store_coef(const FitArgs& A, int b, int i, double ex, double ey) {
+    const int M = A.M, ld = A.ld;
+    const int ci = (i + 1 == M) ? 0 : i + 1;
+    A.cx[at(ci, ld, b)] = ex;
+    A.cy[at(ci, ld, b)] = ey;
+    if (ci < 3) {
+        A.cx[at(M + ci, ld, b)] = ex;
+        A.cy[at(M + ci, ld, b)] = ey;
+    }
+}
+
+STO_HD void fit_part_backsub(const FitArgs& A, int b, int s, int e, double xpx, double xpy, double xkx, double xky) {
+    const int ld = A.ld;
+    fit_store_coef(A, b, e - 1, xkx, xky);
+    double xn = xkx, yn = xky;
+    for (int j0 = e - 2; j0 >= s; j0 -= STO_FIT_CHUNK) {
+        double cs[STO_FIT_CHUNK], xs[STO_FIT_CHUNK], ys[STO_FIT_CHUNK], ls[STO_FIT_CHUNK];
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            cs[k] = xs[k] = ys[k] = ls[k] = 0.0;
+            if (j >= s) {
+                cs[k] = A.cp[at(j, ld, b)]; xs[k] = A.zx[at(j, ld, b)];
+                ys[k] = A.zy[at(j, ld, b)]; ls[k] = A.zz[at(j, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < STO_FIT_CHUNK; ++k) {
+            const int j = j0 - k;
+            if (j < s) break;
+            xn = (xs[k] - ls[k] * xpx) - cs[k] * xn;
+            yn = (ys[k] - ls[k] * xpy) - cs[k] * yn;
+            fit_store_coef(A, b, j, xn, yn);
+        }
+    }
+}
+
+// Number of blocks: a function of M ONLY (never of the batch size or the lane count), so a line's coefficients do not
+// depend on how many lanes happened to share it: 32 blocks from M = 256 on, one block below.
+STO_HD int fit_part_blocks(int M) { return (M >= 256) ? 32 : 1; }
+
+#if defined(__CUDA_ARCH__)
+STO_D PartEq fit_shfl_eq(const PartEq& q, int src) {
+    PartEq r;
+    r.a = __shfl_sync(0xffffffffu, q.a, src);
+    r.d = __shfl_sync(0xffffffffu, q.d, src);
+    r.c = __shfl_sync(0xffffffffu, q.c, src);
+    r.rx = __shfl_sync(0xffffffffu, q.rx, src);
+    r.ry = __shfl_sync(0xffffffffu, q.ry, src);
+    return r;
+}
+STO_D PartFirst fit_shfl_first(const PartFirst& h, int src) {
+    PartFirst r;
+    r.yx = __shfl_sync(0xffffffffu, h.yx, src);
+    r.yy = __shfl_sync(0xffffffffu, h.yy, src);
+    r.wl = __shfl_sync(0xffffffffu, h.wl, src);
+    r.wr = __shfl_sync(0xffffffffu, h.wr, src);
+    return r;
+}
+// Device: lane l of a group of L = P / E lanes that shares candidate b; the lane owns blocks l, l + L, l + 2 L, ...
+// (slot j = block l + j L) and their interface equations.  A PCR step of stride h pairs equation k with k -/+ h: for
+// h < L those sit in lanes l -/+ h (same slot, or the neighbouring slot when the lane index wraps - the SOURCE lane
+// knows whether its one reader wraps and offers the right slot, so each partner costs one set of shuffles); for
+// h >= L they are other slots of the same lane.  Every equation goes through exactly the combines of the emulation
+// below whatever E is, so the result is bit-identical for every lane count.  Whole warps call this.
+template <int E, int P>
+STO_D void fit_solve_partitioned_lane(const FitArgs& A, int b, bool active, int l, int lane0) {
+    constexpr int L = P / E;   // everything below indexes the slot arrays with compile-time values: they stay in registers
+    const int M = A.M;
+    // few slots: every loop over them is unrolled and the slot arrays stay in registers; many slots (big batches, one or
+    // two lanes per line): plain loops over local-memory arrays - the sweeps dominate there and stay compact
+    constexpr int kSweepUnroll = (E <= 4) ? E : 1;
+    constexpr int kStepUnroll = (E <= 4) ? 5 : 1;
+    PartFwd f[E];
+    PartFirst h[E];
+#pragma unroll kSweepUnroll
+    for (int j = 0; j < E; ++j) {
+        f[j] = PartFwd{0.0, 0.0, 0.0, 0.0};
+        h[j] = PartFirst{0.0, 0.0, 0.0, 0.0};
+        if (active) {
+            const int k = l + j * L;
+            const int s = fit_part_begin(M, k, P), e = fit_part_begin(M, k + 1, P);
+            f[j] = fit_part_forward(A, b, s, e);
+            h[j] = fit_part_first(A, b, s, e, f[j]);
+        }
+    }
+    PartEq q[E];
+    {   // block k + 1 is slot j of lane l + 1, or slot j + 1 of lane 0 when l is the last lane
+        const int nl = lane0 + ((l + 1) & (L - 1));
+#pragma unroll kSweepUnroll
+        for (int j = 0; j < E; ++j) {
+            const PartFirst offer = (l == 0) ? h[(j + 1) % E] : h[j];   // lane 0's reader is the last lane: it wraps
+            const PartFirst hn = fit_shfl_first(offer, nl);
+            q[j] = PartEq{0.0, 1.0, 0.0, 0.0, 0.0};
+            if (active) q[j] = fit_part_equation(A, b, fit_part_begin(M, l + j * L + 1, P), f[j], hn);
+        }
+    }
+#pragma unroll kStepUnroll
+    for (int hh = 1; 2 * hh < P; hh <<= 1) {
+        PartEq n[E];
+        if (hh < L) {
+            const int lo_l = lane0 + ((l + L - hh) & (L - 1)), hi_l = lane0 + ((l + hh) & (L - 1));
+            const bool lo_reader_wraps = l >= L - hh;   // my reader l + hh - L < hh reads me as its k - h partner
+            const bool hi_reader_wraps = l < hh;        // my reader l - hh + L reads me as its k + h partner
+#pragma unroll kSweepUnroll
+            for (int j = 0; j < E; ++j) {
+                const PartEq lo = fit_shfl_eq(lo_reader_wraps ? q[(j + E - 1) % E] : q[j], lo_l);
+                const PartEq hi = fit_shfl_eq(hi_reader_wraps ? q[(j + 1) % E] : q[j], hi_l);
+                n[j] = fit_pcr_combine(q[j], lo, hi);
+            }
+        } else {
+            const int m = hh / L;   // partners are m slots away in this lane (compile-time after unrolling)
+#pragma unroll kSweepUnroll
+            for (int j = 0; j < E; ++j) n[j] = fit_pcr_combine(q[j], q[(j + E - m) % E], q[(j + m) % E]);
+        }
+#pragma unroll kSweepUnroll
+        for (int j = 0; j < E; ++j) q[j] = n[j];
+    }
+    double x[E], y[E];
+    if (P >= 2) {
+        constexpr int hh = P / 2;
+        if (hh < L) {   // E == 1: the partner is lane l + L/2, no wrap distinction (both directions reach the same lane)
+#pragma unroll kSweepUnroll
+            for (int j = 0; j < E; ++j) {
+                const PartEq o = fit_shfl_eq(q[j], lane0 + ((l + hh) & (L - 1)));
+                fit_pcr_final(q[j], o, x[j], y[j]);
+            }
+        } else {
+            const int m = hh / L;
+#pragma unroll kSweepUnroll
+            for (int j = 0; j < E; ++j) fit_pcr_final(q[j], q[(j + m) % E], x[j], y[j]);
+        }
+    } else {
+        fit_pcr_single(q[0], x[0], y[0]);
+    }
+    {   // X_{k-1}: slot j of lane l - 1, or slot j - 1 of the last lane when l == 0
+        const int pl = lane0 + ((l + L - 1) & (L - 1));
+#pragma unroll kSweepUnroll
+        for (int j = 0; j < E; ++j) {
+            const bool reader_wraps = (l == L - 1);     // my reader is lane 0
+            const double ox = reader_wraps ? x[(j + E - 1) % E] : x[j], oy = reader_wraps ? y[(j + E - 1) % E] : y[j];
+            const double xpx = __shfl_sync(0xffffffffu, ox, pl), xpy = __shfl_sync(0xffffffffu, oy, pl);
+            if (active) {
+                const int k = l + j * L;
+                fit_part_backsub(A, b, fit_part_begin(M, k, P), fit_part_begin(M, k + 1, P), xpx, xpy, x[j], y[j]);
+            }
+        }
+    }
+}
+// E = blocks per lane (the caller launches G = 32 / E lanes per candidate when M >= 256, one lane below).
+template <int E>
+STO_D void fit_solve_partitioned_group(const FitArgs& A, int b, bool active, int g, int lane0) {
+    if (fit_part_blocks(A.M) == 1) {   // tiny tracks: one block, one lane (any other lanes of the group idle)
+        fit_solve_partitioned_lane<1, 1>(A, b, active && g == 0, 0, lane0 + g);
+        return;
+    }
+    fit_solve_partitioned_lane<E, 32>(A, b, active, g, lane0);
+}
+#endif
+
+// The same schedule played by one caller (host emulation for the tests; also the reference for what the lanes do).
+STO_HD void fit_solve_partitioned_emulated(const FitArgs& A, int b, int P) {
+    const int M = A.M;
+    PartFwd f[32];
+    PartFirst h[32];
+    PartEq q[32], qn[32];
+    double x[32], y[32];
+    for (int g = 0; g < P; ++g) {
+        const int s = fit_part_begin(M, g, P), e = fit_part_begin(M, g + 1, P);
+        f[g] = fit_part_forward(A, b, s, e);
+        h[g] = fit_part_first(A, b, s, e, f[g]);
+    }
+    for (int g = 0; g < P; ++g) q[g] = fit_part_equation(A, b, fit_part_begin(M, g + 1, P), f[g], h[(g + 1) & (P - 1)]);
+    for (int hh = 1; 2 * hh < P; hh <<= 1) {
+        for (int g = 0; g < P; ++g) qn[g] = fit_pcr_combine(q[g], q[(g + P - hh) & (P - 1)], q[(g + hh) & (P - 1)]);
+        for (int g = 0; g < P; ++g) q[g] = qn[g];
+    }
+    for (int g = 0; g < P; ++g) {
+        if (P >= 2) fit_pcr_final(q[g], q[(g + P / 2) & (P - 1)], x[g], y[g]);
+        else fit_pcr_single(q[g], x[g], y[g]);
+    }
+    for (int g = 0; g < P; ++g) {
+        const int s = fit_part_begin(M, g, P), e = fit_part_begin(M, g + 1, P);
+        const int pv = (g + P - 1) & (P - 1);
+        fit_part_backsub(A, b, s, e, x[pv], y[pv], x[g], y[g]);
+    }
+}
+
 STO_HD void fit_degenerate(const FitArgs& A, int b) {  // FITPACK returns ier=10; scipy raises
     const int M = A.M, ld = A.ld;
     if (A.status) A.status[b] |= STO_CAND_DEGENERATE_FIT;
@@ -311,14 +669,18 @@ STO_HD void fit_degenerate(const FitArgs& A, int b) {  // FITPACK returns ier=10
 }
 
 // One lane of a group of G (device).  Lanes 0..2 run the three recurrences when G >= 3.
+// PART_E = 0: Thomas recurrences; PART_E > 0: partitioned solve with PART_E blocks per lane (device only).
+template <int PART_E = 0>
 STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int G, int lane0) {
     (void)lane0;
     if (active) fit_phase_segments(A, b, g, G);
     STO_FIT_SYNC();
     double total = 0.0;
-    if (active && g == 0) total = fit_phase_cumsum(A, b);
 #if defined(__CUDA_ARCH__)
-    total = __shfl_sync(0xffffffffu, total, lane0);
+    if (G > 1) total = fit_phase_cumsum_group(A, b, active, g, G, lane0);
+    else if (active) total = fit_phase_cumsum(A, b);
+#else
+    if (active && g == 0) total = fit_phase_cumsum(A, b);
 #endif
     const bool ok = total > 0.0;
     STO_FIT_SYNC();
@@ -327,6 +689,12 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
     STO_FIT_SYNC();
     if (active && ok) fit_phase_rows(A, b, g, G);
     STO_FIT_SYNC();
+#if defined(__CUDA_ARCH__)
+    if (PART_E > 0) {   // the G lanes solve the cyclic system together
+        fit_solve_partitioned_group<(PART_E > 0) ? PART_E : 1>(A, b, active && ok, g, lane0);
+        return;
+    }
+#endif
     if (active && ok) {
         if (G >= 3) { if (g < 3) fit_phase_thomas(A, b, g); }
         else if (g == 0) fit_phase_thomas_all(A, b);
@@ -345,12 +713,13 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
 
 // Whole fit by one caller: G = 1 is the plain one-lane fit; G > 1 plays the lanes of a group one after another (host
 // emulation of the device schedule, used by the tests).
-STO_HD void fit_candidate(const FitArgs& A, int b, int G = 1) {
+STO_HD void fit_candidate(const FitArgs& A, int b, int G = 1, bool part = false) {
     for (int g = 0; g < G; ++g) fit_phase_segments(A, b, g, G);
     const double total = fit_phase_cumsum(A, b);
     if (!(total > 0.0)) { fit_degenerate(A, b); return; }
     for (int g = 0; g < G; ++g) fit_phase_normalise(A, b, g, G, total);
     for (int g = 0; g < G; ++g) fit_phase_rows(A, b, g, G);
+    if (part) { fit_solve_partitioned_emulated(A, b, fit_part_blocks(A.M)); return; }
     if (G >= 3) {
         for (int w = 0; w < 3; ++w) fit_phase_thomas(A, b, w);
         for (int w = 0; w < 3; ++w) fit_phase_backsub(A, b, w);

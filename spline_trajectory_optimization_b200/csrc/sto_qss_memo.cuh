@@ -61,6 +61,8 @@ static long long g_memo_words[2] = {0, 0};
 static long long g_att_hist[2][16] = {};
 static long long g_sp_visits[2] = {0, 0}, g_sp_distinct[2] = {0, 0}, g_sp_on_live_orig[2] = {0, 0};
 static long long g_sp_evals[2] = {0, 0}, g_sp_changed[2] = {0, 0}, g_sp_maxlist[2] = {0, 0};
+static int g_log_phase = 0, g_log_iter = 0, g_log_on = 0;   // event log: {iteration, sub-pass, sample p, outcome}
+static std::vector<int> g_log;
 #endif
 
 STO_HD int ctz64(u64 x) {
@@ -251,6 +253,9 @@ STO_HD bool apply_res(const QssArgs& A, const MemoCtx& C, int b, bool fwd, int p
     const int N = A.N, d = fwd ? 1 : 0;
     spawn = false;
     changed = false;
+#if defined(STO_HOSTSIM_COUNTERS)
+    if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(p); g_log.push_back(r.kind); }
+#endif
     switch (r.kind) {
         case EV_KILL: return true;
         case EV_ZERO: status |= STO_CAND_ZERO_SPEED; return true;
@@ -829,21 +834,30 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
+#if defined(STO_HOSTSIM_COUNTERS)
+#define STO_LOG_PHASE(k) { g_log_phase = (k); g_log_iter = iters; }
+#else
+#define STO_LOG_PHASE(k)
+#endif
+        STO_LOG_PHASE(0)
         if (G > 1)
             memo_bwd_rows_group<G>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status,
                                    g, lane0);
         else
             memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
         STO_CLK(1)
+        STO_LOG_PHASE(1)
         const int wB = (G > 1)
             ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0)
             : memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
+        STO_LOG_PHASE(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
             memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status STO_SUB_ARG);
         }
         STO_CLK(3)
+        STO_LOG_PHASE(3)
         int wF;
         {
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)

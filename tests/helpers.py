@@ -38,6 +38,21 @@ def test_vehicle_params():
 test_vehicle_params.__test__ = False
 
 
+def knots_from_u(u):
+    """FITPACK's periodic knot vector from the chord-length parameter u[0..M] (u[M] = 1): three knots wrapped on each side."""
+    u = np.asarray(u, dtype=np.float64)
+    M = len(u) - 1
+    return np.concatenate([u[M - 3:M] - 1.0, u, u[1:4] + 1.0])
+
+
+def oracle_lap_from_coefficients(O, u, cx, cy, ts, sinb, veh, ref_pow=0):
+    """Lap time of one line through the oracle's sampler + QSS + fill_time, starting from GIVEN spline coefficients
+    (whatever solver produced them): the bit-exact check of everything downstream of the fit."""
+    X, Y, YAW, R = O.sample(knots_from_u(u), cx, cy, 3, ts, ref_pow)
+    sb = np.zeros(len(ts)) if sinb is None else np.asarray(sinb, dtype=np.float64)
+    return O.qss(X, Y, R, sb, veh, ref_pow)["lap"]
+
+
 def to_sm(a_cm, device="cuda"):
     """[B, n] host candidate-major -> [n, round_up(B, 32)] device sample-major (zero padded)."""
     import torch

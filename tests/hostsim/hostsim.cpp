@@ -25,7 +25,7 @@ int hostsim_fit(const double* cenx, const double* ceny, const double* nrmx, cons
     A.cenx = cenx; A.ceny = ceny; A.nrmx = nrmx; A.nrmy = nrmy; A.off = off; A.px = px; A.py = py;
     A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
     A.cp = w.data(); A.zx = A.cp + (size_t)M * ld; A.zy = A.zx + (size_t)M * ld; A.zz = A.zy + (size_t)M * ld;
-    for (int b = 0; b < B; ++b) sto::fit_candidate(A, b, split);
+    for (int b = 0; b < B; ++b) sto::fit_candidate(A, b, split < 0 ? -split : split, split < 0);   // split < 0: partitioned solve over |split| lanes
     return 0;
 }
 
@@ -128,6 +128,11 @@ void hostsim_sp_counters(long long* out12, int reset) {
                          sto::g_sp_maxlist};
     for (int k = 0; k < 6; ++k) { out12[2 * k] = src[k][0]; out12[2 * k + 1] = src[k][1]; if (reset) src[k][0] = src[k][1] = 0; }
 }
+
+// event log of the memoised schedule (analysis tooling): 4 ints per applied outcome
+void hostsim_log_enable(int on) { sto::g_log_on = on; sto::g_log.clear(); }
+long long hostsim_log_size(void) { return (long long)sto::g_log.size(); }
+void hostsim_log_copy(int* out) { memcpy(out, sto::g_log.data(), sto::g_log.size() * sizeof(int)); }
 
 void hostsim_att_hist(long long* out32) {
     for (int d = 0; d < 2; ++d) for (int k = 0; k < 16; ++k) { out32[d * 16 + k] = sto::g_att_hist[d][k]; sto::g_att_hist[d][k] = 0; }

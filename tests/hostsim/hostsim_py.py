@@ -75,7 +75,7 @@ def fit_points(points, split=1):
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 
-def fit_offsets(cenx, ceny, nrmx, nrmy, offsets):
+def fit_offsets(cenx, ceny, nrmx, nrmy, offsets, split=1):
     off = np.asarray(offsets, dtype=np.float64)
     B, M = off.shape
     o = sm(off)
@@ -83,7 +83,7 @@ def fit_offsets(cenx, ceny, nrmx, nrmy, offsets):
     u, cx, cy = np.empty((M + 1, B)), np.empty((M + 3, B)), np.empty((M + 3, B))
     st = np.zeros(B, dtype=np.int32)
     lib().hostsim_fit(_p(cenx), _p(ceny), _p(nrmx), _p(nrmy), _p(o), None, None, M, B, B, _p(u), _p(cx), _p(cy),
-                      st.ctypes.data_as(_ip), 1)
+                      st.ctypes.data_as(_ip), int(split))
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 

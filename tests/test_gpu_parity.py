@@ -8,6 +8,8 @@ within 1e-6 s on identical inputs.  What is actually asserted is tighter:
   * against the reference's golden vectors on identical inputs: speeds <= 1e-12 relative (libm pow(x,2) vs x*x),
     laps <= 1e-9 s; end to end through our own fit: lap <= 1e-6 s (speeds deviate <= ~3e-8).
 """
+import contextlib
+
 import numpy as np
 import pytest
 
@@ -16,7 +18,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 import oracle_py as O  # noqa: E402
-from helpers import (CAND_CASES, SIM_CASES, golden, rel_err, test_vehicle_params, to_cm, to_sm,  # noqa: E402
+from helpers import (CAND_CASES, SIM_CASES, golden, oracle_lap_from_coefficients, rel_err,  # noqa: E402
+                     test_vehicle_params, to_cm, to_sm,
                      veh_args)
 
 
@@ -26,6 +29,19 @@ def sto():
     from spline_trajectory_optimization_b200 import _lib, evaluator
     _lib.load()   # fails loudly if libsto_b200.so is missing: there is no fallback
     return evaluator
+
+
+@contextlib.contextmanager
+def fit_solver(name):
+    """'thomas': the one-lane Thomas + Sherman-Morrison recurrences (what oracle/sto_oracle.c's fit restates, so
+    everything is bit-exact against O.lap_batch); 'partitioned': the default lane-group solver."""
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    lib.sto_set_fit_partition(0 if name == "thomas" else -1)
+    try:
+        yield
+    finally:
+        lib.sto_set_fit_partition(-1)
 
 
 def _evaluator(sto, d, ts=None, bank=None, impl="memo"):
@@ -41,7 +57,8 @@ def test_fit_and_sample(sto, name):
     d = golden(name)
     ev = _evaluator(sto, d)
     B, M = d["offsets"].shape
-    u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
+    with fit_solver("thomas"):
+        u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
     S = ev.sample(u, cx, cy, B=B, want=("x", "y", "yaw", "radius", "chord_qss", "chord_norm"))
     torch.cuda.synchronize()
     assert not st[:B].any()
@@ -58,8 +75,14 @@ def test_fit_and_sample(sto, name):
         assert np.max(np.abs(X[b] - d["ref_X"][b])) < 1e-9            # end to end vs the reference's samples
     # fit from explicit points == fit from centre + offset * normal
     px, py = to_sm(d["points"][:, :, 0]), to_sm(d["points"][:, :, 1])
-    u2, cx2, cy2, _ = ev.fit(points_sm=(px, py), B=B)
+    with fit_solver("thomas"):
+        u2, cx2, cy2, _ = ev.fit(points_sm=(px, py), B=B)
     assert np.array_equal(to_cm(cx2, B), cx) and np.array_equal(to_cm(u2, B), u)
+    # default solver: same knots, same samples to 1e-9 (bit-exactness of that path: test_fit_partitioned_on_device)
+    u3, cx3, cy3, _ = ev.fit(to_sm(d["offsets"]), B=B)
+    u4, cx4, cy4, _ = ev.fit(points_sm=(px, py), B=B)
+    assert np.array_equal(to_cm(u3, B), u) and rel_err(to_cm(cx3, B), cx) < 1e-12
+    assert np.array_equal(to_cm(cx4, B), to_cm(cx3, B)) and np.array_equal(to_cm(cy4, B), to_cm(cy3, B))
 
 
 @pytest.mark.parametrize("name", CAND_CASES)
@@ -117,22 +140,31 @@ def test_qss_synthetic_tables(sto, impl):
 
 @pytest.mark.parametrize("name", CAND_CASES)
 @pytest.mark.parametrize("impl", ["plain", "memo"])
-def test_fused_lap_time(sto, name, impl):
+@pytest.mark.parametrize("solver", ["thomas", "partitioned"])
+def test_fused_lap_time(sto, name, impl, solver):
     d = golden(name)
     ev = _evaluator(sto, d, impl=impl)
     B = d["offsets"].shape[0]
-    lap, st = ev.lap_times(to_sm(d["offsets"]), B=B)
-    lap, st = lap.cpu().numpy(), st.cpu().numpy()
-    assert not st.any()
     ov = O.make_vehicle(*veh_args(d))
     nx, ny = -np.sin(d["centre_yaw"]), np.cos(d["centre_yaw"])
     olap, ost = O.lap_batch(d["centre_x"], d["centre_y"], nx, ny, d["offsets"], d["ts"], np.zeros(len(d["ts"])),
                             ov, n_threads=4, ref_pow=0)
-    assert np.array_equal(lap, olap)                                 # bit-exact vs the oracle
-    assert np.max(np.abs(lap - d["ref_lap"])) < 1e-6                  # BASELINE: lap within 1e-6 s of the reference
-    # host-buffer entry point (H2D + transpose + D2H inside) returns the same bits
-    hlap, hst = ev.lap_times_host(d["offsets"])
-    assert np.array_equal(hlap, lap) and not hst.any()
+    with fit_solver(solver):
+        lap, st = ev.lap_times(to_sm(d["offsets"]), B=B)
+        lap, st = lap.cpu().numpy(), st.cpu().numpy()
+        assert not st.any()
+        if solver == "thomas":
+            assert np.array_equal(lap, olap)                             # bit-exact vs the oracle, fit included
+        else:
+            assert np.max(np.abs(lap - olap)) < 1e-7                     # the solvers differ in the last bits of c
+            u, cx, cy, _ = ev.fit(to_sm(d["offsets"]), B=B)             # ... downstream of the fit: bit-exact
+            u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+            for b in range(B):
+                assert lap[b] == oracle_lap_from_coefficients(O, u[b], cx[b], cy[b], d["ts"], None, ov)
+        assert np.max(np.abs(lap - d["ref_lap"])) < 1e-6                  # BASELINE: lap within 1e-6 s of the reference
+        # host-buffer entry point (H2D + transpose + D2H inside) returns the same bits
+        hlap, hst = ev.lap_times_host(d["offsets"])
+        assert np.array_equal(hlap, lap) and not hst.any()
 
 
 def test_simulator_drop_in(sto):
@@ -201,13 +233,19 @@ def test_edge_cases(sto):
     assert int(idx[0]) == int(np.argmin(lap_all.cpu().numpy())) and float(best[0]) == float(lap_all.min())
     # M = 3: the smallest closed line FITPACK accepts (trajectory.py:214)
     tri = np.array([[[0.0, 0.0], [40.0, 0.0], [20.0, 30.0]]])
-    u, cx, cy, st = ev.fit(points_sm=(to_sm(tri[:, :, 0]), to_sm(tri[:, :, 1])), B=1)
     t, ocx, ocy = O.fit_periodic_cubic(tri[0])
-    assert np.array_equal(to_cm(cx, 1)[0], ocx) and int(st[0]) == 0
-    # all points identical -> FITPACK would refuse (ier=10); we flag the candidate instead of aborting the batch
     z = np.zeros((1, 5))
-    u, cx, cy, st = ev.fit(points_sm=(to_sm(z), to_sm(z)), B=1)
-    assert int(st[0]) & _lib.CAND_DEGENERATE_FIT and bool(torch.isnan(cx[:, 0]).all())
+    for solver in ("thomas", "partitioned"):
+        with fit_solver(solver):
+            u, cx, cy, st = ev.fit(points_sm=(to_sm(tri[:, :, 0]), to_sm(tri[:, :, 1])), B=1)
+            assert int(st[0]) == 0 and np.array_equal(to_cm(u, 1)[0], t[3:-3])
+            if solver == "thomas":
+                assert np.array_equal(to_cm(cx, 1)[0], ocx) and np.array_equal(to_cm(cy, 1)[0], ocy)
+            else:
+                assert np.max(np.abs(to_cm(cx, 1)[0] - ocx)) < 1e-12 and np.max(np.abs(to_cm(cy, 1)[0] - ocy)) < 1e-12
+            # all points identical -> FITPACK would refuse (ier=10); we flag the candidate instead of aborting the batch
+            u, cx, cy, st = ev.fit(points_sm=(to_sm(z), to_sm(z)), B=1)
+            assert int(st[0]) & _lib.CAND_DEGENERATE_FIT and bool(torch.isnan(cx[:, 0]).all())
 
 
 def test_full_size_properties(sto):
@@ -230,13 +268,21 @@ def test_full_size_properties(sto):
     g = golden("cand_m2895_n2895")
     assert abs(lap[0] - g["ref_lap"][0]) < 1e-6
     assert 100.0 < lap.min() and lap.max() < 120.0
-    # oracle spot checks, bit-exact
+    # oracle spot checks: bit-exact downstream of the fit (the same lines fitted in a batch of 4 - 32 lanes each instead
+    # of 8 - give the same coefficients), 1e-7 s against the oracle's own (Thomas) fit, bit-exact with the Thomas solver
     ov = O.make_vehicle(*veh_args(g))
     nrm = rt.left_normals()
     pick = [0, 1, 777, 4095]
     olap, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[pick], rt.center_d.ts(),
                           np.zeros(M), ov, n_threads=4, ref_pow=0)
-    assert np.array_equal(lap[pick], olap)
+    assert np.max(np.abs(lap[pick] - olap)) < 1e-7
+    pu, pcx, pcy, _ = ev.fit(to_sm(off[pick]), B=4)
+    pu, pcx, pcy = to_cm(pu, 4), to_cm(pcx, 4), to_cm(pcy, 4)
+    for k, b in enumerate(pick):
+        assert lap[b] == oracle_lap_from_coefficients(O, pu[k], pcx[k], pcy[k], rt.center_d.ts(), None, ov)
+    with fit_solver("thomas"):
+        lap_t, _ = ev.lap_times(d_off, B=B)
+    assert np.array_equal(lap_t.cpu().numpy()[pick], olap)
     # permutation invariance: candidates are independent (what the multi-GPU sharding relies on)
     perm = np.random.default_rng(0).permutation(B)
     lap_p, _ = ev.lap_times(ev.to_sample_major(torch.from_numpy(off[perm]).cuda()), B=B)
@@ -266,9 +312,12 @@ def test_fused_banked_oval(sto):
     laps = {}
     for impl in ("plain", "memo"):
         ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), veh, bank=bank, impl=impl)
-        lap, st = ev.lap_times(to_sm(off), B=B)
+        with fit_solver("thomas"):
+            lap, st = ev.lap_times(to_sm(off), B=B)
         assert not st.cpu().numpy().any()
         laps[impl] = lap.cpu().numpy()
+        lap_d, st_d = ev.lap_times(to_sm(off), B=B)      # default fit solver
+        assert not st_d.cpu().numpy().any() and np.max(np.abs(lap_d.cpu().numpy() - laps[impl])) < 1e-7
     g = golden("cand_m579_n579")
     ov = O.make_vehicle(*veh_args(g))
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
@@ -295,13 +344,99 @@ def test_long_track_quarter_metre(sto):
     off = candidates.smooth_offsets(M, B, rt.dist_to_left, rt.dist_to_right, seed=11)
     nrm = rt.left_normals()
     ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
-    lap, st = ev.lap_times(to_sm(off), B=B)
-    lap = lap.cpu().numpy()
-    assert not st.cpu().numpy().any()
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    lib.sto_set_fit_partition(0)             # one-lane Thomas fit: bit-exact against the oracle's
+    try:
+        lap, st = ev.lap_times(to_sm(off), B=B)
+        lap = lap.cpu().numpy()
+    finally:
+        lib.sto_set_fit_partition(-1)
+    lap_p, st_p = ev.lap_times(to_sm(off), B=B)   # automatic plan: 32 lanes share each candidate's cyclic solve
+    assert lib.sto_fit_partition_lanes(M, B) == 32
+    assert not st.cpu().numpy().any() and not st_p.cpu().numpy().any()
+    assert np.max(np.abs(lap_p.cpu().numpy() - lap)) < 1e-7
     g = golden("cand_m579_n579")
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
                             np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=4, ref_pow=0)
     assert not ost.any() and np.array_equal(lap, olap)
+
+
+def test_fit_partitioned_on_device(sto):
+    """Default fit solver: lane groups solve the cyclic system together (block elimination + PCR over __shfl_sync).
+    Bit-exact against the host emulation for EVERY lane count (the block structure depends on M only, so a line's
+    coefficients never depend on the batch it was evaluated in); knots identical to FITPACK; coefficients within 1e-12
+    of the Thomas solve / 1e-9 of FITPACK; laps bit-exact against the oracle's sampler + QSS run on these coefficients."""
+    import os
+    import hostsim_py as H
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    for name in ("cand_m579_n579", "cand_m2895_n2895"):
+        d = golden(name)
+        ev = _evaluator(sto, d)
+        B, M = d["offsets"].shape
+        assert lib.sto_fit_partition_lanes(M, B) == 32 and lib.sto_fit_partition_lanes(M, 4096) == 8
+        assert lib.sto_fit_partition_lanes(M, 1 << 20) == 1 and lib.sto_fit_partition_lanes(100, 4) == 1
+        hu, hcx, hcy, _ = H.fit_points(d["points"], -1)
+        try:
+            for lanes in (32, 16, 8, 4, 2, 1):
+                os.environ["STO_FIT_SPLIT"] = str(lanes)
+                u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
+                torch.cuda.synchronize()
+                assert not st[:B].any()
+                u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+                assert np.array_equal(u, hu) and np.array_equal(cx, hcx) and np.array_equal(cy, hcy), lanes
+        finally:
+            del os.environ["STO_FIT_SPLIT"]
+        lap1, st1 = ev.lap_times(to_sm(d["offsets"]), B=B)
+        lib.sto_set_fit_partition(0)
+        try:
+            assert lib.sto_fit_partition_lanes(M, B) == 0
+            u0, cx0, cy0, _ = ev.fit(to_sm(d["offsets"]), B=B)
+            lap0, _ = ev.lap_times(to_sm(d["offsets"]), B=B)
+            torch.cuda.synchronize()
+        finally:
+            lib.sto_set_fit_partition(-1)
+        assert np.array_equal(u, to_cm(u0, B))
+        assert rel_err(cx, to_cm(cx0, B)) < 1e-12 and rel_err(cy, to_cm(cy0, B)) < 1e-12
+        assert rel_err(cx, d["ref_cx"]) < 1e-9 and rel_err(cy, d["ref_cy"]) < 1e-9
+        lap1 = lap1[:B].cpu().numpy()
+        assert not st1[:B].cpu().numpy().any()
+        assert np.max(np.abs(lap1 - lap0[:B].cpu().numpy())) < 1e-7
+        assert np.max(np.abs(lap1 - d["ref_lap"])) < 1e-6
+        ov = O.make_vehicle(*veh_args(d))
+        for b in range(B):
+            assert lap1[b] == oracle_lap_from_coefficients(O, u[b], cx[b], cy[b], d["ts"], None, ov)
+
+
+def test_fit_partitioned_quarter_metre(sto):
+    """BASELINE config 5 fit size (M = 23,160): 32 lanes per line for a small batch, fewer as the batch grows - with
+    identical bits; equal to the host emulation bit for bit and to the oracle's Thomas solve within 1e-12."""
+    import hostsim_py as H
+    from spline_trajectory_optimization_b200 import _lib, candidates, tracks
+    from spline_trajectory_optimization_b200.models.race_track import RaceTrack
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    lib = _lib.load()
+    c, l, r = tracks.monza_raw()
+    rt = RaceTrack("monza", l, r, c, s=10.0, interval=0.25)
+    M = len(rt.center_d)
+    nrm = rt.left_normals()
+    ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
+    assert lib.sto_fit_partition_lanes(M, 4) == 32 and lib.sto_fit_partition_lanes(M, 20000) == 4
+    off = candidates.smooth_offsets(M, 600, rt.dist_to_left, rt.dist_to_right, seed=3)
+    hu, hcx, hcy, _ = H.fit_offsets(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:3], split=-1)
+    for B in (1, 3, 70, 600):       # 32, 32, 32 and 16 lanes per line
+        u, cx, cy, st = ev.fit(to_sm(off[:B]), B=B)
+        torch.cuda.synchronize()
+        assert not st[:B].any()
+        u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+        nb = min(B, 3)
+        assert np.array_equal(u[:nb], hu[:nb]) and np.array_equal(cx[:nb], hcx[:nb]) and np.array_equal(cy[:nb], hcy[:nb])
+    pts = rt.center_d[None, :, :2] + off[:3, :, None] * nrm[None]
+    for b in range(3):
+        t, ocx, ocy = O.fit_periodic_cubic(pts[b])
+        assert np.array_equal(hu[b], t[3:-3])
+        assert rel_err(hcx[b], ocx) < 1e-12 and rel_err(hcy[b], ocy) < 1e-12
 
 
 def test_status_flags_and_chunked_host_path(sto):

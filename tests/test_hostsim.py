@@ -6,7 +6,7 @@ import pytest
 
 import hostsim_py as H
 import oracle_py as O
-from helpers import CAND_CASES, SIM_CASES, golden, veh_args
+from helpers import CAND_CASES, SIM_CASES, golden, rel_err, veh_args
 
 
 @pytest.mark.parametrize("name", CAND_CASES[:2])
@@ -143,3 +143,38 @@ def test_arc_sections_gauss_legendre(name):
     bwd = np.cumsum(sec)
     assert bwd[0] == 0.0
     assert np.max(np.abs(bwd[1:] - d["in_DIST_BWD"][1:]) / d["in_DIST_BWD"][1:]) < 1e-9
+
+
+@pytest.mark.parametrize("name", CAND_CASES)
+def test_fit_partitioned_solver(name):
+    """Default fit solver (sto_fit.cuh, partitioned cyclic solve): 32 blocks of rows eliminated independently, the
+    interface system solved by parallel cyclic reduction.  Same knots bit for bit; coefficients equal to the one-lane
+    Thomas solve up to rounding and within BASELINE's 1e-9 of FITPACK; independent of how the row work is split."""
+    d = golden(name)
+    u0, cx0, cy0, _ = H.fit_points(d["points"], 1)
+    ref = None
+    for lanes in (1, 4, 32):
+        u, cx, cy, st = H.fit_points(d["points"], -lanes)
+        assert not st.any() and np.array_equal(u, u0)
+        assert rel_err(cx, cx0) < 1e-12 and rel_err(cy, cy0) < 1e-12
+        assert rel_err(cx, d["ref_cx"]) < 1e-9 and rel_err(cy, d["ref_cy"]) < 1e-9
+        assert np.array_equal(cx[:, -3:], cx[:, :3]) and np.array_equal(cy[:, -3:], cy[:, :3])   # periodic wrap
+        ref = (cx, cy) if ref is None else ref
+        assert np.array_equal(cx, ref[0]) and np.array_equal(cy, ref[1])
+
+
+def test_fit_partitioned_ragged_and_tiny():
+    """Blocks of unequal length, the shortest blocks (8 rows at M = 256), single-block tracks (M < 256) and strongly
+    non-uniform spacing."""
+    rng = np.random.default_rng(5)
+    for M in (4, 7, 16, 64, 255, 256, 257, 1000, 4099):
+        th = np.sort(rng.uniform(0, 2 * np.pi, M))
+        th[1::3] = th[::3][:len(th[1::3])] + 1e-3 * rng.uniform(0.1, 1.0, len(th[1::3]))   # clustered points
+        th = np.sort(th)
+        pts = np.stack([np.cos(th) * (1 + 0.1 * rng.standard_normal(M)), 0.7 * np.sin(th)], -1)[None]
+        u0, cx0, cy0, st0 = H.fit_points(pts, 1)
+        assert not st0.any()
+        scale = np.abs(cx0).max()
+        u, cx, cy, st = H.fit_points(pts, -1)
+        assert not st.any() and np.array_equal(u, u0)
+        assert np.max(np.abs(cx - cx0)) < 1e-10 * scale and np.max(np.abs(cy - cy0)) < 1e-10 * scale, M

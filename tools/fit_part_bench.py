@@ -1,0 +1,64 @@
+"""Developer tool (GPU): fit kernel time on a long track (Monza at 0.25 m, M = 23,160) - one-lane Thomas solve vs the
+partitioned lane-group solve - for several batch sizes.  python tools/fit_part_bench.py [interval_m]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import test_vehicle_params, to_sm  # noqa: E402
+from spline_trajectory_optimization_b200 import _lib, candidates, tracks  # noqa: E402
+from spline_trajectory_optimization_b200.evaluator import BatchedLineEvaluator  # noqa: E402
+from spline_trajectory_optimization_b200.models.race_track import RaceTrack  # noqa: E402
+from spline_trajectory_optimization_b200.models.vehicle import Vehicle  # noqa: E402
+
+interval = float(sys.argv[1]) if len(sys.argv) > 1 else 0.25
+lib = _lib.load()
+c, l, r = tracks.monza_raw()
+rt = RaceTrack("monza", l, r, c, s=10.0, interval=interval)
+M = len(rt.center_d)
+ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), Vehicle(test_vehicle_params()))
+base = candidates.smooth_offsets(M, 64, rt.dist_to_left, rt.dist_to_right, seed=3)
+if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_bench.py 0.25 with SWEEP=1
+    for B in (256, 1024, 4096, 16384):
+        off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
+        line = f"M={M} B={B:6d}"
+        for mode, lanes in ((0, 1), (0, 8), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
+            os.environ["STO_FIT_SPLIT"] = str(lanes)
+            lib.sto_set_fit_partition(mode)
+            best = 1e9
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ev.fit(off, B=B)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            line += f"  {'part' if mode else 'thomas'}x{lanes}: {best:8.2f} ms"
+        print(line, flush=True)
+    del os.environ["STO_FIT_SPLIT"]
+    lib.sto_set_fit_partition(-1)
+    sys.exit(0)
+for B in (1, 64, 1024, 4096, 16384):
+    off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
+    res = {}
+    for mode, name in ((0, "one-lane"), (1, "partitioned")):
+        lib.sto_set_fit_partition(mode)
+        lanes = lib.sto_fit_partition_lanes(M, B)
+        best = 1e9
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            u, cx, cy, st = ev.fit(off, B=B)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        res[name] = (best, lanes, cx[:, :B].clone())
+    lib.sto_set_fit_partition(-1)
+    a, b = res["one-lane"], res["partitioned"]
+    err = float(((a[2] - b[2]).abs().max() / a[2].abs().max()).item())
+    print(f"M={M} B={B:6d}  one-lane {a[0]:9.3f} ms   partitioned ({b[1]:2d} lanes) {b[0]:9.3f} ms   speed-up {a[0] / b[0]:6.2f}x   "
+          f"auto plan lanes {lib.sto_fit_partition_lanes(M, B)}   max |dc|/|c| {err:.2e}", flush=True)
