@@ -159,6 +159,17 @@ STO_HD size_t memo_smem_bytes(int N, int cands) {
     return memo_plane_bytes(N) * (size_t)cands + (size_t)STO_LIST_RING * 32 * sizeof(int32_t);
 }
 
+#if defined(__CUDA_ARCH__)
+// Single-bit atomics on a 64-bit plane word, issued as native 32-bit atomics on the half that holds the bit (a 64-bit
+// atomicAnd / atomicOr on shared memory compiles to a compare-and-swap loop; 7 % of the kernel's stall samples).
+STO_D void atom_set_bit(const Ring& r, int pos) {
+    atomicOr(reinterpret_cast<unsigned*>(r.m + (size_t)(pos >> 6) * r.stride) + ((pos >> 5) & 1), 1u << (pos & 31));
+}
+STO_D void atom_clear_bit(const Ring& r, int pos) {
+    atomicAnd(reinterpret_cast<unsigned*>(r.m + (size_t)(pos >> 6) * r.stride) + ((pos >> 5) & 1), ~(1u << (pos & 31)));
+}
+#endif
+
 // Clears bits {a, a+1 (mod N)} of one plane: one read-modify-write when both fall into the same 64-bit word.
 STO_HD void clear_pair(const Ring& r, int a, int a1) {
     if ((a >> 6) == (a1 >> 6)) {
@@ -483,32 +494,27 @@ STO_HD void memo_bwd_rows_group(const QssArgs& A, const MemoWork& W, const MemoC
                                      res.kind == EV_RESPAWN || res.kind == EV_ZERO);
         const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
         const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
-        const u64 pbit = 1ull << (p & 63);
-        u64* const contw = cont.m + (size_t)(p >> 6) * cont.stride;
-        u64* const stopw = stop.m + (size_t)(p >> 6) * stop.stride;
         if (changed) {
             double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
             rq[0] = res.v_new;
             rq[1] = res.a_new;
         }
         if (has) {
-            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atomicOr(contw, pbit); atomicAnd(stopw, ~pbit); }
-            else if (res.kind == EV_STOP) { atomicOr(stopw, pbit); atomicAnd(contw, ~pbit); }
-            else if (res.kind == EV_SPAWN) { atomicAnd(contw, ~pbit); atomicAnd(stopw, ~pbit); }
-            if (stopped) atomicAnd(live.m + (size_t)w * live.stride, ~(1ull << kth_bit(att, g)));
+            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atom_set_bit(cont, p); atom_clear_bit(stop, p); }
+            else if (res.kind == EV_STOP) { atom_set_bit(stop, p); atom_clear_bit(cont, p); }
+            else if (res.kind == EV_SPAWN) { atom_clear_bit(cont, p); atom_clear_bit(stop, p); }
+            if (stopped) atom_clear_bit(live, 64 * w + kth_bit(att, g));
         }
         __syncwarp();
         if (changed) {
             const int qp = (q == 0) ? N - 1 : q - 1;
-            const u64 qbit = 1ull << (q & 63);
-            atomicAnd(cont.m + (size_t)(q >> 6) * cont.stride, ~qbit);            // edge q -> q-1
-            atomicAnd(stop.m + (size_t)(q >> 6) * stop.stride, ~qbit);
+            atom_clear_bit(cont, q);                                              // edge q -> q-1
+            atom_clear_bit(stop, q);
             const Ring cf = C.cont(1), sf = C.stop(1);
-            atomicAnd(cf.m + (size_t)(q >> 6) * cf.stride, ~qbit);                // edge q -> q+1
-            atomicAnd(sf.m + (size_t)(q >> 6) * sf.stride, ~qbit);
-            const u64 qpbit = 1ull << (qp & 63);
-            atomicAnd(cf.m + (size_t)(qp >> 6) * cf.stride, ~qpbit);              // edge q-1 -> q
-            atomicAnd(sf.m + (size_t)(qp >> 6) * sf.stride, ~qpbit);
+            atom_clear_bit(cf, q);                                                // edge q -> q+1
+            atom_clear_bit(sf, q);
+            atom_clear_bit(cf, qp);                                               // edge q-1 -> q
+            atom_clear_bit(sf, qp);
         }
         {   // bookkeeping mirrored on every lane of the group
             const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
@@ -721,34 +727,30 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
         const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
         const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
         if (has) {
-            const u64 pbit = 1ull << (p & 63);
-            u64* const contw = cont.m + (size_t)(p >> 6) * cont.stride;
-            u64* const stopw = stop.m + (size_t)(p >> 6) * stop.stride;
             if (changed) {
                 double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
                 rq[0] = res.v_new;
                 rq[1] = res.a_new;
             }
-            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atomicOr(contw, pbit); atomicAnd(stopw, ~pbit); }
-            else if (res.kind == EV_STOP) { atomicOr(stopw, pbit); atomicAnd(contw, ~pbit); }
-            else if (res.kind == EV_SPAWN) { atomicAnd(contw, ~pbit); atomicAnd(stopw, ~pbit); }
+            if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atom_set_bit(cont, p); atom_clear_bit(stop, p); }
+            else if (res.kind == EV_STOP) { atom_set_bit(stop, p); atom_clear_bit(cont, p); }
+            else if (res.kind == EV_SPAWN) { atom_clear_bit(cont, p); atom_clear_bit(stop, p); }
             if (stopped) list[at(slot, ld, b)] = -1;
         }
         __syncwarp();
         if (changed) {   // memo_invalidate(q) minus this front's own edge (bit p of its own direction's planes)
             const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
             const Ring cb = C.cont(0), sb = C.stop(0), cf = C.cont(1), sf = C.stop(1);
-            const u64 qbit = 1ull << (q & 63), qnbit = 1ull << (qn & 63), qpbit = 1ull << (qp & 63);
-            atomicAnd(cb.m + (size_t)(q >> 6) * cb.stride, ~qbit);                    // edge q -> q-1
-            atomicAnd(sb.m + (size_t)(q >> 6) * sb.stride, ~qbit);
-            atomicAnd(cf.m + (size_t)(q >> 6) * cf.stride, ~qbit);                    // edge q -> q+1
-            atomicAnd(sf.m + (size_t)(q >> 6) * sf.stride, ~qbit);
+            atom_clear_bit(cb, q);                                                    // edge q -> q-1
+            atom_clear_bit(sb, q);
+            atom_clear_bit(cf, q);                                                    // edge q -> q+1
+            atom_clear_bit(sf, q);
             if (FWD) {   // own edge is p -> q = (q-1 -> q): skip it, clear q+1 -> q
-                atomicAnd(cb.m + (size_t)(qn >> 6) * cb.stride, ~qnbit);
-                atomicAnd(sb.m + (size_t)(qn >> 6) * sb.stride, ~qnbit);
+                atom_clear_bit(cb, qn);
+                atom_clear_bit(sb, qn);
             } else {     // own edge is p -> q = (q+1 -> q): skip it, clear q-1 -> q
-                atomicAnd(cf.m + (size_t)(qp >> 6) * cf.stride, ~qpbit);
-                atomicAnd(sf.m + (size_t)(qp >> 6) * sf.stride, ~qpbit);
+                atom_clear_bit(cf, qp);
+                atom_clear_bit(sf, qp);
             }
         }
         {
