@@ -63,13 +63,14 @@ int pick_fit_split(int B) {
 //   B =  1024: Thomas x8 3.6 | 32.8   partitioned x16 0.64 |  7.7   (x32 0.58 | 11.3)
 //   B =  4096: Thomas x8 4.2 | 34.3   partitioned x8  1.81 | 16.1
 //   B = 16384: Thomas x1 8.8 | 71.2   partitioned x4  3.60 | 29.8
+//   B = 32768: Thomas x2 8.7          partitioned x2  5.9          B = 65536: Thomas x1 11.4, partitioned x1 9.2
 int g_fit_part = -1;
 struct FitPlan { int split; bool part; };
 FitPlan pick_fit_plan(int M, int B) {
     int mode = g_fit_part;
     if (const char* e = getenv("STO_FIT_PART")) mode = atoi(e);
     if (mode == 0) return FitPlan{pick_fit_split(B), false};
-    int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 32768) ? 4 : (B <= 131072) ? 2 : 1;
+    int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 24576) ? 4 : (B <= 49152) ? 2 : 1;
     if (const char* e = getenv("STO_FIT_SPLIT")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;

@@ -391,6 +391,22 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                 if (stop.test(p)) { L &= ~bit; --nlive; att &= ~donemask; continue; }
                 q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
                 pending = true;
+#if defined(STO_HOSTSIM_COUNTERS)
+                if (g_log_on && FWD) {   // analysis: is this front separated from the previous evaluated one by a dead row?
+                    static int last_row = -1, last_iter = -1;
+                    const int row = 64 * w + t;
+                    int gap = 1;
+                    if (last_iter == g_log_iter && last_row >= 0 && last_row < row) {
+                        gap = 0;
+                        for (int rr = last_row + 1; rr < row; ++rr) {
+                            const bool alive = (rr >> 6) == w ? ((L >> (rr & 63)) & 1ull) : live.test(rr);
+                            if (!alive) { gap = 1; break; }
+                        }
+                    }
+                    g_log.push_back(g_log_iter); g_log.push_back(10 + gap); g_log.push_back(row); g_log.push_back(0);
+                    last_row = row; last_iter = g_log_iter;
+                }
+#endif
                 break;
             }
         }
@@ -879,7 +895,8 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
             for (int j = 0; j < nnew; ++j) {
                 const int ivb = W.spB[at(nB + j, ld, b)];   // (q + s + 1) mod N
-                int ivf = (ivb - 2 * (s + 1)) % N;            // (q - (s + 1)) mod N
+                int ivf = ivb - 2 * (s + 1);                  // (q - (s + 1)) mod N: in [-2N, N), no integer division
+                if (ivf < 0) ivf += N;
                 if (ivf < 0) ivf += N;
                 W.spB[at(wB + j, ld, b)] = ivb;
                 W.spF[at(wF + j, ld, b)] = ivf;

@@ -422,7 +422,7 @@ def test_fit_partitioned_quarter_metre(sto):
     M = len(rt.center_d)
     nrm = rt.left_normals()
     ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
-    assert lib.sto_fit_partition_lanes(M, 4) == 32 and lib.sto_fit_partition_lanes(M, 20000) == 4
+    assert lib.sto_fit_partition_lanes(M, 4) == 32 and lib.sto_fit_partition_lanes(M, 20000) == 4 and lib.sto_fit_partition_lanes(M, 40000) == 2
     off = candidates.smooth_offsets(M, 600, rt.dist_to_left, rt.dist_to_right, seed=3)
     hu, hcx, hcy, _ = H.fit_offsets(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:3], split=-1)
     for B in (1, 3, 70, 600):       # 32, 32, 32 and 16 lanes per line

@@ -72,3 +72,31 @@ if __name__ == "__main__":
     for ph, name, fwd in ((0, "B-orig", False), (1, "B-spawn", False), (2, "F-orig", True), (3, "F-spawn", True)):
         n, tot, longest = chain_stats(ev, N, ph, fwd)
         print(f"{name:8s} evals {n:6d}  rounds lower bound by lanes {tot}  longest chain {longest}")
+
+
+def forig_run_schedule(ev, G=(1, 2, 4, 8, 16, 32)):
+    """F-orig under the exact 'live-run' rule: evaluated fronts separated by a dead row are independent chains; a run of
+    live rows is one sequential chain.  Rounds = greedy list scheduling of the chains of each sub-pass on G lanes."""
+    e = ev[(ev[:, 1] == 10) | (ev[:, 1] == 11)]
+    tot = {g: 0 for g in G}
+    nchains = 0
+    for it in np.unique(e[:, 0]):
+        x = e[e[:, 0] == it]
+        chains = []
+        for _, ph, row, _ in x:
+            if ph == 11 or not chains:
+                chains.append(0)
+            chains[-1] += 1
+        nchains += len(chains)
+        for g in G:
+            lanes = [0] * g
+            for c in chains:                       # in row order, next free lane
+                k = int(np.argmin(lanes))
+                lanes[k] += c
+            tot[g] += max(lanes)
+    return len(e), nchains, tot
+
+
+if __name__ == "__main__":
+    n, nch, tot = forig_run_schedule(ev)
+    print(f"F-orig live-run rule: {n} evaluations in {nch} chains; rounds by lanes {tot}")

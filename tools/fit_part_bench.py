@@ -23,10 +23,10 @@ M = len(rt.center_d)
 ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), Vehicle(test_vehicle_params()))
 base = candidates.smooth_offsets(M, 64, rt.dist_to_left, rt.dist_to_right, seed=3)
 if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_bench.py 0.25 with SWEEP=1
-    for B in (256, 1024, 4096, 16384):
+    for B in [int(x) for x in os.environ.get("SWEEP_B", "256,1024,4096,16384").split(",")]:
         off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
         line = f"M={M} B={B:6d}"
-        for mode, lanes in ((0, 1), (0, 8), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
+        for mode, lanes in ((0, 1), (0, 2), (0, 8), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
             os.environ["STO_FIT_SPLIT"] = str(lanes)
             lib.sto_set_fit_partition(mode)
             best = 1e9
