@@ -112,6 +112,22 @@ int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, c
                                const double* py, int M, int B, int ld, double* u, double* cx, double* cy,
                                int32_t* status, void* work, size_t work_bytes, void* stream);
 
+/* ---- non-interpolating candidates: least-squares closed spline on FIXED knots ------------------------------ */
+/*
+ * The reference smooths a line with BSplineTrajectory(coords, s > 0, k) (models/trajectory.py:213-223 -> splprep ->
+ * FITPACK clocur), whose knots come out of an adaptive iteration.  For a batch the knot vector is held fixed - the
+ * knots t[nt] (device) of the track's own smoothing fit, models/race_track.py:23-29 - and every candidate gets FITPACK's
+ * task = -1 fit on them: chord-length parameter u as above, then the degree-k (1..5) periodic least-squares spline,
+ * = scipy.interpolate.splprep([x, y], task=-1, t=t, k=k, per=1).  Outputs: u[M+1][ld], cx, cy [nt-k-1][ld] in SciPy's
+ * order (last k coefficients repeat the first k): feed them to sto_sample_splines_f64 / sto_lap_time_splines_f64.
+ * A knot interval without data sets STO_CAND_DEGENERATE_FIT for that candidate (FITPACK: ier = 10) and NaN coefficients.
+ */
+size_t sto_fit_lsq_workspace_bytes(int M, int nt, int k, int B);
+int sto_fit_periodic_lsq_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                             const double* normal_y, const double* offsets, const double* px, const double* py,
+                             int M, int B, int ld, const double* t, int nt, int k, double* u, double* cx, double* cy,
+                             int32_t* status, void* work, size_t work_bytes, void* stream);
+
 /* ---- sample_along(ts=...) + yaw + turn radius: models/trajectory.py:250-260,268-281 ---------------- */
 /*
  * Evaluates every candidate spline (its own knot vector u) at the shared parameters ts[N] in SciPy's
@@ -206,6 +222,10 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
  * best_lap[0], best_idx[0] (device).  Ties resolve to the lowest index. */
 int sto_argmin_f64(const double* lap, const int32_t* status, int B, double* best_lap, int64_t* best_idx,
                    void* stream);
+
+/* FP64 pipe peak of the current device in TFLOP/s (2 flops per DFMA; 8 independent chains per thread, every SM full;
+ * best of 3 timed launches, synchronous): the denominator of bench.py's FP64 utilisation figure. */
+int sto_measure_fp64_peak(double* tflops);
 
 /* [B][M] candidate-major <-> [M][ld] sample-major transposes on the device (layout adapters). */
 int sto_transpose_f64(const double* src, int rows, int cols, int ld_src, double* dst, int ld_dst, void* stream);

@@ -56,10 +56,14 @@ _SIGNATURES = {
                                    C.c_size_t, _vp]),
     "sto_lap_time_host_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [C.POINTER(StoVehicle), C.c_int, _vp, _vp,
                                         C.c_int, C.c_size_t]),
+    "sto_fit_lsq_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "sto_fit_periodic_lsq_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [_vp, C.c_int, C.c_int] + [_vp] * 5 +
+                                 [C.c_size_t, _vp]),
     "sto_set_stage_timing": (C.c_int, [C.c_int]),
     "sto_set_fit_partition": (None, [C.c_int]),
     "sto_fit_partition_lanes": (C.c_int, [C.c_int, C.c_int]),
     "sto_last_stage_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "sto_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
     "sto_argmin_f64": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "sto_transpose_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
 }

@@ -13,6 +13,7 @@
 #include "sto_common.cuh"
 #include "sto_eval.cuh"
 #include "sto_fit.cuh"
+#include "sto_fit_lsq.cuh"
 #include "sto_qss.cuh"
 #include "sto_qss_memo.cuh"
 
@@ -179,6 +180,12 @@ void launch_fit(const sto::FitArgs& A, const FitPlan& plan, cudaStream_t st) {
     }
 }
 
+// Least-squares closed spline on fixed knots (sto_fit_lsq.cuh), one candidate per thread, coalesced sample-major.
+__global__ void fit_lsq_kernel(sto::LsqArgs A) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < A.F.B) sto::lsq_candidate_k(A, b);
+}
+
 // `split` lanes share a candidate, each taking a contiguous slice of its samples (samples are independent): small
 // batches get split x more threads, which is what a latency-bound kernel needs.
 __global__ void eval_kernel(sto::EvalArgs A, int split) {
@@ -276,6 +283,18 @@ __global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const 
     int32_t* ring = reinterpret_cast<int32_t*>(sto_planes + (size_t)6 * W.W * cpw);
     const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, ring, 32, lane, A.N, W.W);
     sto::qss_memo_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G);
+}
+
+// FP64 pipe peak for the roofline report: 8 independent DFMA chains per thread, every SM full.
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = a + threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3, x4 = x0 + 4e-3, x5 = x0 + 5e-3,
+           x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, b, a); x1 = __fma_rn(x1, b, a); x2 = __fma_rn(x2, b, a); x3 = __fma_rn(x3, b, a);
+        x4 = __fma_rn(x4, b, a); x5 = __fma_rn(x5, b, a); x6 = __fma_rn(x6, b, a); x7 = __fma_rn(x7, b, a);
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456) out[0] = r;   // never true: keeps the chains alive
 }
 
 __global__ void zero_status_kernel(int32_t* s, int B) {
@@ -519,6 +538,42 @@ int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, c
     return STO_OK;
 }
 
+size_t sto_fit_lsq_workspace_bytes(int M, int nt, int k, int B) {
+    if (B < 1 || !sto::lsq_sizes_ok(M, nt, k)) return 0;
+    return sto::lsq_work_doubles(nt, k) * ldof(B) * sizeof(double) + 256;
+}
+
+int sto_fit_periodic_lsq_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                             const double* normal_y, const double* offsets, const double* px, const double* py,
+                             int M, int B, int ld, const double* t, int nt, int k, double* u, double* cx, double* cy,
+                             int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (!sto::lsq_sizes_ok(M, nt, k))
+        return fail(STO_ERR_INVALID, "least-squares fit needs 1 <= k <= 5, nt - 2k - 1 >= 3k + 1 free coefficients, M >= that");
+    if (B < 1 || ld < B) return fail(STO_ERR_INVALID, "need B >= 1 and ld >= B");
+    if (!t || !u || !cx || !cy || !work) return fail(STO_ERR_INVALID, "t, u, cx, cy, work must be non-NULL");
+    const bool frenet = centre_x != nullptr;
+    if (frenet && (!centre_y || !normal_x || !normal_y || !offsets))
+        return fail(STO_ERR_INVALID, "centre/normal/offsets must all be given");
+    if (!frenet && (!px || !py)) return fail(STO_ERR_INVALID, "either centre+normal+offsets or px+py");
+    const size_t g = (size_t)(nt - 2 * k - 1);
+    if (sto::lsq_work_doubles(nt, k) * (size_t)ld * sizeof(double) + 256 > work_bytes)
+        return fail(STO_ERR_WORKSPACE, "least-squares fit workspace too small (sto_fit_lsq_workspace_bytes; ld = round_up(B, 32))");
+    Carver c(work);
+    sto::LsqArgs A{};
+    A.F.cenx = centre_x; A.F.ceny = centre_y; A.F.nrmx = normal_x; A.F.nrmy = normal_y; A.F.off = offsets;
+    A.F.px = px; A.F.py = py; A.F.M = M; A.F.B = B; A.F.ld = ld; A.F.u = u; A.F.status = status;
+    A.t = t; A.nt = nt; A.k = k; A.cx = cx; A.cy = cy;
+    A.band = c.take<double>(sto::lsq_work_doubles(nt, k) * (size_t)ld);
+    A.rx = A.band + g * (size_t)(k + 1) * ld;
+    A.ry = A.rx + g * ld;
+    A.Y = A.ry + g * ld;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int block = (B >= 148 * 128) ? 128 : 32;
+    fit_lsq_kernel<<<grid_for(B, block), block, 0, st>>>(A);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
 int sto_sample_f64(const double* u, const double* cx, const double* cy, int M, const double* ts, int N, int B,
                    int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
                    double* chord_norm, void* stream) {
@@ -750,6 +805,34 @@ int sto_transpose_f64(const double* src, int rows, int cols, int ld_src, double*
     dim3 g((cols + 31) / 32, (rows + 31) / 32), blk(32, 8);
     transpose_kernel<<<g, blk, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, dst, ld_dst);
     STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_measure_fp64_peak(double* tflops) {
+    if (!tflops) return fail(STO_ERR_INVALID, "tflops is NULL");
+    int dev = 0, sms = 0;
+    STO_CUDA(cudaGetDevice(&dev));
+    STO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    STO_CUDA(cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    STO_CUDA(cudaEventCreate(&e0));
+    STO_CUDA(cudaEventCreate(&e1));
+    const int iters = 1 << 15, block = 256, grid = sms * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first pass warms up
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<grid, block>>>(out, iters, 1e-9, 0.999999);
+        cudaEventRecord(e1);
+        STO_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = 2.0 * 8.0 * (double)iters * (double)block * (double)grid / ((double)best * 1e-3) / 1e12;
     return STO_OK;
 }
 

@@ -240,6 +240,48 @@ class BatchedLineEvaluator:
                                                           _ptr(work), work.numel(), _stream()))
         return u, cx, cy, st
 
+    def fit_lsq(self, knots, k, offsets_sm=None, B=None, points_sm=None):
+        """Non-interpolating candidates: the degree-k periodic least-squares spline of every
+        line on the SHARED knot vector `knots` (host array, e.g. the knots of the track's own smoothing fit) - per
+        candidate equal to ``scipy.interpolate.splprep([x, y], task=-1, t=knots, k=k, per=1)``, FITPACK's fixed-knot
+        variant of the reference's ``BSplineTrajectory(coords, s, k)`` (models/trajectory.py:213-223).
+        Returns u[M+1, ld], cx[nt-k-1, ld], cy[nt-k-1, ld], status[ld]; feed cx, cy to lap_times_splines / sample_splines."""
+        src = offsets_sm if offsets_sm is not None else points_sm[0]
+        M, ld = src.shape
+        B = ld if B is None else int(B)
+        dev = self.device
+        t = np.ascontiguousarray(knots, dtype=np.float64)
+        nt, k = len(t), int(k)
+        nbytes = self.lib.sto_fit_lsq_workspace_bytes(M, nt, k, B)
+        if nbytes == 0:
+            raise ValueError("fit_lsq: needs 1 <= k <= 5 and 3k + 1 <= len(knots) - 2k - 1 <= M")
+        u = torch.empty((M + 1, ld), dtype=torch.float64, device=dev)
+        cx = torch.empty((nt - k - 1, ld), dtype=torch.float64, device=dev)
+        cy = torch.empty((nt - k - 1, ld), dtype=torch.float64, device=dev)
+        st = torch.zeros(ld, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            d_t = torch.from_numpy(t).to(dev)
+            work = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            if offsets_sm is not None:
+                assert M == self.M
+                args = (_ptr(self.d["cx"]), _ptr(self.d["cy"]), _ptr(self.d["nx"]), _ptr(self.d["ny"]),
+                        _ptr(offsets_sm), None, None)
+            else:
+                args = (None, None, None, None, None, _ptr(points_sm[0]), _ptr(points_sm[1]))
+            _lib.check(self.lib.sto_fit_periodic_lsq_f64(*args, M, B, ld, _ptr(d_t), nt, k, _ptr(u), _ptr(cx), _ptr(cy),
+                                                         _ptr(st), _ptr(work), work.numel(), _stream()))
+            torch.cuda.current_stream().synchronize()   # d_t and work are temporaries of this call
+        return u, cx, cy, st
+
+    def lap_times_lsq(self, knots, k, offsets_sm, B=None):
+        """Smoothed candidates end to end: fit_lsq -> sample_along(ts) on the shared knots -> QSS -> lap time."""
+        M, ld = offsets_sm.shape
+        B = ld if B is None else int(B)
+        u, cx, cy, st = self.fit_lsq(knots, k, offsets_sm=offsets_sm, B=B)
+        lap, st2 = lap_times_splines(knots, k, cx, cy, self.ts_host, self.vehicle, B=B, sin_bank=self.sinb_host,
+                                     impl=self.impl)
+        return lap, (st[:B] | st2)
+
     def sample(self, u, cx, cy, B=None, ts=None, want=("x", "y", "yaw", "radius")):
         """sample_along(ts=...) for every candidate.  Returns dict of [N, ld] tensors."""
         M, ld = u.shape[0] - 1, u.shape[1]

@@ -12,6 +12,7 @@
 #include "../../spline_trajectory_optimization_b200/csrc/sto_common.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_eval.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_fit.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_fit_lsq.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss_memo.cuh"
 
@@ -26,6 +27,23 @@ int hostsim_fit(const double* cenx, const double* ceny, const double* nrmx, cons
     A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
     A.cp = w.data(); A.zx = A.cp + (size_t)M * ld; A.zy = A.zx + (size_t)M * ld; A.zz = A.zy + (size_t)M * ld;
     for (int b = 0; b < B; ++b) sto::fit_candidate(A, b, split < 0 ? -split : split, split < 0);   // split < 0: partitioned solve over |split| lanes
+    return 0;
+}
+
+// least-squares periodic fit on fixed knots (sto_fit_lsq.cuh); px, py [M][ld]; outputs u [M+1][ld], cx, cy [nt-k-1][ld]
+int hostsim_fit_lsq(const double* px, const double* py, int M, int B, int ld, const double* t, int nt, int k, double* u,
+                    double* cx, double* cy, int32_t* status) {
+    if (!sto::lsq_sizes_ok(M, nt, k)) return -1;
+    std::vector<double> w(sto::lsq_work_doubles(nt, k) * (size_t)ld);
+    const size_t g = (size_t)(nt - 2 * k - 1);
+    sto::LsqArgs A{};
+    A.F.px = px; A.F.py = py; A.F.M = M; A.F.B = B; A.F.ld = ld; A.F.u = u; A.F.status = status;
+    A.t = t; A.nt = nt; A.k = k; A.cx = cx; A.cy = cy;
+    A.band = w.data();
+    A.rx = A.band + g * (size_t)(k + 1) * ld;
+    A.ry = A.rx + g * ld;
+    A.Y = A.ry + g * ld;
+    for (int b = 0; b < B; ++b) sto::lsq_candidate_k(A, b);
     return 0;
 }
 

@@ -37,7 +37,7 @@ def make_vehicle(scalars, acc_x, acc_c, dcc_x, dcc_c):
 def build():
     srcs = [os.path.join(HERE, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "..", "spline_trajectory_optimization_b200", "csrc", f)
-        for f in ("sto_common.cuh", "sto_fit.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh")]
+        for f in ("sto_common.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-o", LIB, srcs[0]])
     return LIB
@@ -84,6 +84,22 @@ def fit_offsets(cenx, ceny, nrmx, nrmy, offsets, split=1):
     st = np.zeros(B, dtype=np.int32)
     lib().hostsim_fit(_p(cenx), _p(ceny), _p(nrmx), _p(nrmy), _p(o), None, None, M, B, B, _p(u), _p(cx), _p(cy),
                       st.ctypes.data_as(_ip), int(split))
+    return u.T.copy(), cx.T.copy(), cy.T.copy(), st
+
+
+def fit_lsq(points, t, k):
+    """points[B, M, 2], shared knots t[nt], degree k -> u[B, M+1], cx[B, nt-k-1], cy[B, nt-k-1], status[B]"""
+    pts = np.asarray(points, dtype=np.float64)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    B, M, _ = pts.shape
+    nc = len(t) - k - 1
+    px, py = sm(pts[:, :, 0]), sm(pts[:, :, 1])
+    u, cx, cy = np.empty((M + 1, B)), np.empty((nc, B)), np.empty((nc, B))
+    st = np.zeros(B, dtype=np.int32)
+    rc = lib().hostsim_fit_lsq(_p(px), _p(py), M, B, B, _p(t), len(t), int(k), _p(u), _p(cx), _p(cy),
+                               st.ctypes.data_as(_ip))
+    if rc != 0:
+        raise ValueError("unsupported sizes for the least-squares fit")
     return u.T.copy(), cx.T.copy(), cy.T.copy(), st
 
 

@@ -178,3 +178,44 @@ def test_fit_partitioned_ragged_and_tiny():
         u, cx, cy, st = H.fit_points(pts, -1)
         assert not st.any() and np.array_equal(u, u0)
         assert np.max(np.abs(cx - cx0)) < 1e-10 * scale and np.max(np.abs(cy - cy0)) < 1e-10 * scale, M
+
+
+@pytest.mark.parametrize("k,s", [(3, 10.0), (5, 30.0), (1, 50.0), (4, 20.0)])
+def test_fit_lsq_matches_fitpack_fixed_knots(k, s):
+    """least-squares closed spline on fixed knots (sto_fit_lsq.cuh) == FITPACK task = -1
+    (scipy.interpolate.splprep(task=-1, t=knots, per=1)) on the knots of a smoothing fit, every degree; 1e-9 is the
+    BASELINE tolerance for coefficients, 1e-12 is what the bordered Cholesky solve delivers."""
+    import warnings
+    from scipy.interpolate import splprep
+    d = golden("cand_m2895_n2895")
+    pts = d["points"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = np.vstack([pts[0], pts[0][:1]])
+        t = splprep([c0[:, 0], c0[:, 1]], s=s, k=k, per=1)[0][0]
+        u, cx, cy, st = H.fit_lsq(pts, t, k)
+        assert not st.any() and cx.shape[1] == len(t) - k - 1
+        for b in range(len(pts)):
+            c = np.vstack([pts[b], pts[b][:1]])
+            (tt, (rx, ry), kk), ru = splprep([c[:, 0], c[:, 1]], task=-1, t=t, k=k, per=1)
+            assert np.array_equal(u[b], ru)                                   # chord-length parameter: bit-identical
+            assert np.max(np.abs(cx[b] - rx)) < 1e-12 * np.max(np.abs(rx))
+            assert np.max(np.abs(cy[b] - ry)) < 1e-12 * np.max(np.abs(ry))
+            assert np.array_equal(cx[b, -k:], cx[b, :k]) and np.array_equal(cy[b, -k:], cy[b, :k])
+
+
+def test_fit_lsq_flags_empty_knot_interval():
+    """A knot interval without data: FITPACK returns ier = 10; the candidate is flagged, its neighbours are not."""
+    d = golden("cand_m579_n579")
+    pts = d["points"][:2].copy()
+    k = 3
+    inner = np.linspace(0.0, 1.0, 41)
+    inner = np.sort(np.concatenate([inner, [0.50001, 0.50002, 0.50003, 0.50004, 0.50005]]))   # five knots between two data points
+    per = 1.0
+    t = np.concatenate([inner[-k - 1:-1] - per, inner, inner[1:k + 1] + per])
+    u, cx, cy, st = H.fit_lsq(pts, t, k)
+    assert st.all() and np.isnan(cx).all()
+    inner = np.linspace(0.0, 1.0, 41)
+    t = np.concatenate([inner[-k - 1:-1] - per, inner, inner[1:k + 1] + per])
+    u, cx, cy, st = H.fit_lsq(pts, t, k)
+    assert not st.any() and np.isfinite(cx).all()
