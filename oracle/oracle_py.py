@@ -92,6 +92,12 @@ def maxlat(veh, lon, ref_pow=1):
     return lib().sto_oracle_maxlat(C.byref(veh), float(lon), int(ref_pow))
 
 
+def set_fit_solver(name):
+    """'blocks' (default): 32-block elimination + cyclic reduction, the CUDA library's default solver; 'thomas': one-lane
+    Thomas + Sherman-Morrison (library: sto_set_fit_partition(0)).  Applies to fit_periodic_cubic and lap_batch."""
+    lib().sto_oracle_set_fit_solver({"blocks": 1, "thomas": 0}[name])
+
+
 def fit_periodic_cubic(points):
     pts = _f64(points)
     M = pts.shape[0]

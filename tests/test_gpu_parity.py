@@ -33,15 +33,18 @@ def sto():
 
 @contextlib.contextmanager
 def fit_solver(name):
-    """'thomas': the one-lane Thomas + Sherman-Morrison recurrences (what oracle/sto_oracle.c's fit restates, so
-    everything is bit-exact against O.lap_batch); 'partitioned': the default lane-group solver."""
+    """Selects the solver of the cyclic collocation system in the library AND in the oracle, which restates both:
+    'thomas' = one-lane Thomas + Sherman-Morrison recurrences, 'partitioned' = the default (32 blocks + cyclic reduction,
+    lane groups on the device).  With matching solvers everything is bit-exact against O.lap_batch."""
     from spline_trajectory_optimization_b200 import _lib
     lib = _lib.load()
     lib.sto_set_fit_partition(0 if name == "thomas" else -1)
+    O.set_fit_solver("thomas" if name == "thomas" else "blocks")   # the oracle restates both solvers
     try:
         yield
     finally:
         lib.sto_set_fit_partition(-1)
+        O.set_fit_solver("blocks")
 
 
 def _evaluator(sto, d, ts=None, bank=None, impl="memo"):
@@ -53,12 +56,17 @@ def _evaluator(sto, d, ts=None, bank=None, impl="memo"):
 
 
 @pytest.mark.parametrize("name", CAND_CASES)
-def test_fit_and_sample(sto, name):
+@pytest.mark.parametrize("solver", ["thomas", "partitioned"])
+def test_fit_and_sample(sto, name, solver):
+    with fit_solver(solver):
+        _fit_and_sample(sto, name)
+
+
+def _fit_and_sample(sto, name):
     d = golden(name)
     ev = _evaluator(sto, d)
     B, M = d["offsets"].shape
-    with fit_solver("thomas"):
-        u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
+    u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
     S = ev.sample(u, cx, cy, B=B, want=("x", "y", "yaw", "radius", "chord_qss", "chord_norm"))
     torch.cuda.synchronize()
     assert not st[:B].any()
@@ -75,14 +83,8 @@ def test_fit_and_sample(sto, name):
         assert np.max(np.abs(X[b] - d["ref_X"][b])) < 1e-9            # end to end vs the reference's samples
     # fit from explicit points == fit from centre + offset * normal
     px, py = to_sm(d["points"][:, :, 0]), to_sm(d["points"][:, :, 1])
-    with fit_solver("thomas"):
-        u2, cx2, cy2, _ = ev.fit(points_sm=(px, py), B=B)
+    u2, cx2, cy2, _ = ev.fit(points_sm=(px, py), B=B)
     assert np.array_equal(to_cm(cx2, B), cx) and np.array_equal(to_cm(u2, B), u)
-    # default solver: same knots, same samples to 1e-9 (bit-exactness of that path: test_fit_partitioned_on_device)
-    u3, cx3, cy3, _ = ev.fit(to_sm(d["offsets"]), B=B)
-    u4, cx4, cy4, _ = ev.fit(points_sm=(px, py), B=B)
-    assert np.array_equal(to_cm(u3, B), u) and rel_err(to_cm(cx3, B), cx) < 1e-12
-    assert np.array_equal(to_cm(cx4, B), to_cm(cx3, B)) and np.array_equal(to_cm(cy4, B), to_cm(cy3, B))
 
 
 @pytest.mark.parametrize("name", CAND_CASES)
@@ -153,14 +155,14 @@ def test_fused_lap_time(sto, name, impl, solver):
         lap, st = ev.lap_times(to_sm(d["offsets"]), B=B)
         lap, st = lap.cpu().numpy(), st.cpu().numpy()
         assert not st.any()
-        if solver == "thomas":
-            assert np.array_equal(lap, olap)                             # bit-exact vs the oracle, fit included
-        else:
-            assert np.max(np.abs(lap - olap)) < 1e-7                     # the solvers differ in the last bits of c
-            u, cx, cy, _ = ev.fit(to_sm(d["offsets"]), B=B)             # ... downstream of the fit: bit-exact
-            u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
-            for b in range(B):
-                assert lap[b] == oracle_lap_from_coefficients(O, u[b], cx[b], cy[b], d["ts"], None, ov)
+        olap_s, _ = O.lap_batch(d["centre_x"], d["centre_y"], nx, ny, d["offsets"], d["ts"], np.zeros(len(d["ts"])),
+                                ov, n_threads=4, ref_pow=0)
+        assert np.array_equal(lap, olap_s)                               # bit-exact vs the oracle, fit included
+        assert np.max(np.abs(lap - olap)) < 1e-7                         # the two solvers: last bits of c only
+        u, cx, cy, _ = ev.fit(to_sm(d["offsets"]), B=B)                 # downstream of the fit from GIVEN coefficients
+        u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+        for b in range(B):
+            assert lap[b] == oracle_lap_from_coefficients(O, u[b], cx[b], cy[b], d["ts"], None, ov)
         assert np.max(np.abs(lap - d["ref_lap"])) < 1e-6                  # BASELINE: lap within 1e-6 s of the reference
         # host-buffer entry point (H2D + transpose + D2H inside) returns the same bits
         hlap, hst = ev.lap_times_host(d["offsets"])
@@ -233,16 +235,13 @@ def test_edge_cases(sto):
     assert int(idx[0]) == int(np.argmin(lap_all.cpu().numpy())) and float(best[0]) == float(lap_all.min())
     # M = 3: the smallest closed line FITPACK accepts (trajectory.py:214)
     tri = np.array([[[0.0, 0.0], [40.0, 0.0], [20.0, 30.0]]])
-    t, ocx, ocy = O.fit_periodic_cubic(tri[0])
     z = np.zeros((1, 5))
     for solver in ("thomas", "partitioned"):
         with fit_solver(solver):
+            t, ocx, ocy = O.fit_periodic_cubic(tri[0])
             u, cx, cy, st = ev.fit(points_sm=(to_sm(tri[:, :, 0]), to_sm(tri[:, :, 1])), B=1)
             assert int(st[0]) == 0 and np.array_equal(to_cm(u, 1)[0], t[3:-3])
-            if solver == "thomas":
-                assert np.array_equal(to_cm(cx, 1)[0], ocx) and np.array_equal(to_cm(cy, 1)[0], ocy)
-            else:
-                assert np.max(np.abs(to_cm(cx, 1)[0] - ocx)) < 1e-12 and np.max(np.abs(to_cm(cy, 1)[0] - ocy)) < 1e-12
+            assert np.array_equal(to_cm(cx, 1)[0], ocx) and np.array_equal(to_cm(cy, 1)[0], ocy)
             # all points identical -> FITPACK would refuse (ier=10); we flag the candidate instead of aborting the batch
             u, cx, cy, st = ev.fit(points_sm=(to_sm(z), to_sm(z)), B=1)
             assert int(st[0]) & _lib.CAND_DEGENERATE_FIT and bool(torch.isnan(cx[:, 0]).all())
@@ -268,21 +267,22 @@ def test_full_size_properties(sto):
     g = golden("cand_m2895_n2895")
     assert abs(lap[0] - g["ref_lap"][0]) < 1e-6
     assert 100.0 < lap.min() and lap.max() < 120.0
-    # oracle spot checks: bit-exact downstream of the fit (the same lines fitted in a batch of 4 - 32 lanes each instead
-    # of 8 - give the same coefficients), 1e-7 s against the oracle's own (Thomas) fit, bit-exact with the Thomas solver
+    # oracle spot checks, bit-exact (fit included; the same lines fitted in a batch of 4 use 32 lanes each instead of 8
+    # and still give the same bits), with either solver of the collocation system
     ov = O.make_vehicle(*veh_args(g))
     nrm = rt.left_normals()
     pick = [0, 1, 777, 4095]
     olap, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[pick], rt.center_d.ts(),
                           np.zeros(M), ov, n_threads=4, ref_pow=0)
-    assert np.max(np.abs(lap[pick] - olap)) < 1e-7
-    pu, pcx, pcy, _ = ev.fit(to_sm(off[pick]), B=4)
-    pu, pcx, pcy = to_cm(pu, 4), to_cm(pcx, 4), to_cm(pcy, 4)
-    for k, b in enumerate(pick):
-        assert lap[b] == oracle_lap_from_coefficients(O, pu[k], pcx[k], pcy[k], rt.center_d.ts(), None, ov)
+    assert np.array_equal(lap[pick], olap)
+    lap4, _ = ev.lap_times(to_sm(off[pick]), B=4)
+    assert np.array_equal(lap4.cpu().numpy(), olap)
     with fit_solver("thomas"):
         lap_t, _ = ev.lap_times(d_off, B=B)
-    assert np.array_equal(lap_t.cpu().numpy()[pick], olap)
+        olap_t, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[pick], rt.center_d.ts(),
+                                np.zeros(M), ov, n_threads=4, ref_pow=0)
+    assert np.array_equal(lap_t.cpu().numpy()[pick], olap_t)
+    assert np.max(np.abs(olap_t - olap)) < 1e-7
     # permutation invariance: candidates are independent (what the multi-GPU sharding relies on)
     perm = np.random.default_rng(0).permutation(B)
     lap_p, _ = ev.lap_times(ev.to_sample_major(torch.from_numpy(off[perm]).cuda()), B=B)
@@ -312,12 +312,12 @@ def test_fused_banked_oval(sto):
     laps = {}
     for impl in ("plain", "memo"):
         ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), veh, bank=bank, impl=impl)
-        with fit_solver("thomas"):
-            lap, st = ev.lap_times(to_sm(off), B=B)
+        lap, st = ev.lap_times(to_sm(off), B=B)
         assert not st.cpu().numpy().any()
         laps[impl] = lap.cpu().numpy()
-        lap_d, st_d = ev.lap_times(to_sm(off), B=B)      # default fit solver
-        assert not st_d.cpu().numpy().any() and np.max(np.abs(lap_d.cpu().numpy() - laps[impl])) < 1e-7
+        with fit_solver("thomas"):
+            lap_t, st_t = ev.lap_times(to_sm(off), B=B)
+        assert not st_t.cpu().numpy().any() and np.max(np.abs(lap_t.cpu().numpy() - laps[impl])) < 1e-7
     g = golden("cand_m579_n579")
     ov = O.make_vehicle(*veh_args(g))
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
@@ -346,20 +346,20 @@ def test_long_track_quarter_metre(sto):
     ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
     from spline_trajectory_optimization_b200 import _lib
     lib = _lib.load()
-    lib.sto_set_fit_partition(0)             # one-lane Thomas fit: bit-exact against the oracle's
-    try:
-        lap, st = ev.lap_times(to_sm(off), B=B)
-        lap = lap.cpu().numpy()
-    finally:
-        lib.sto_set_fit_partition(-1)
-    lap_p, st_p = ev.lap_times(to_sm(off), B=B)   # automatic plan: 32 lanes share each candidate's cyclic solve
+    lap, st = ev.lap_times(to_sm(off), B=B)       # automatic plan: 32 lanes share each candidate's cyclic solve
     assert lib.sto_fit_partition_lanes(M, B) == 32
-    assert not st.cpu().numpy().any() and not st_p.cpu().numpy().any()
-    assert np.max(np.abs(lap_p.cpu().numpy() - lap)) < 1e-7
+    lap = lap.cpu().numpy()
+    assert not st.cpu().numpy().any()
     g = golden("cand_m579_n579")
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
                             np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=4, ref_pow=0)
     assert not ost.any() and np.array_equal(lap, olap)
+    with fit_solver("thomas"):               # the one-lane Thomas chain of 23 k rows
+        lap_t, st_t = ev.lap_times(to_sm(off[:2]), B=2)
+        olap_t, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:2], rt.center_d.ts(),
+                                np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=2, ref_pow=0)
+    assert not st_t.cpu().numpy().any() and np.array_equal(lap_t.cpu().numpy(), olap_t)
+    assert np.max(np.abs(olap_t - olap[:2])) < 1e-6
 
 
 def test_fit_partitioned_on_device(sto):

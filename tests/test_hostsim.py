@@ -9,10 +9,19 @@ import oracle_py as O
 from helpers import CAND_CASES, SIM_CASES, golden, rel_err, veh_args
 
 
+@pytest.fixture(autouse=True)
+def _default_oracle_solver():
+    yield
+    O.set_fit_solver("blocks")
+
+
 @pytest.mark.parametrize("name", CAND_CASES[:2])
-def test_fit_and_eval_bit_exact(name):
+@pytest.mark.parametrize("solver", ["thomas", "blocks"])
+def test_fit_and_eval_bit_exact(name, solver):
+    """Host build of the device fit (both solvers) == the oracle's restatement of the same solver, bit for bit."""
     d = golden(name)
-    u, cx, cy, st = H.fit_points(d["points"])
+    O.set_fit_solver(solver)
+    u, cx, cy, st = H.fit_points(d["points"], 1 if solver == "thomas" else -1)
     assert not st.any()
     E = H.evaluate(u, cx, cy, d["ts"])
     for b in range(d["points"].shape[0]):
