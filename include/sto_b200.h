@@ -96,17 +96,25 @@ int sto_release(void);                /* frees the device arena cached by the *_
  * are read from px, py ([M][ld] each).  Outputs (device, sample-major): u[M+1][ld] chord-length parameter
  * (knots are t[0..2] = u[M-3..M-1]-1, t[3+j] = u[j], t[M+4..M+6] = u[1..3]+1), cx, cy [M+3][ld] B-spline
  * coefficients in SciPy's order (c[M..M+2] = c[0..2]).
- * `work` needs sto_fit_workspace_bytes(M, B) bytes.
+ * `work` needs sto_fit_workspace_bytes(M, B) bytes (five [M][ld] arrays).
  */
 size_t sto_fit_workspace_bytes(int M, int B);
-/* Solver of the cyclic tridiagonal collocation system.  Default (mode -1 or 1): a group of up to 32 lanes shares each
- * candidate - block elimination per lane with the interface unknowns kept symbolic, the interface system by parallel
- * cyclic reduction over __shfl_sync, one division per row; the lane count follows the batch size (32 for a few long
- * lines, 1 for batches that fill the GPU on their own).  mode 0: one-lane Thomas + Sherman-Morrison recurrences, the
- * solver oracle/sto_oracle.c restates (bit-identical to it).  Same knots either way; coefficients agree to ~1e-15
- * relative, both within 3e-14 of FITPACK on the golden lines. */
-void sto_set_fit_partition(int mode);
-int sto_fit_partition_lanes(int M, int B);   /* lanes per candidate of the partitioned solve; 0 = Thomas solver selected */
+/* Solver of the interpolation system.
+ *   STO_FIT_FITPACK (default): FITPACK's own arithmetic - fpclos for s = 0, k = 3: fpbspl values, Givens rotations of
+ *     the M observation rows into a band triangle (fpgivs / fprota), the periodic wrap carried in a dense M x 2 block,
+ *     back substitution fpbacp - restated operation by operation.  u, cx, cy are BIT-IDENTICAL to
+ *     scipy.interpolate.splprep(per=1, s=0, k=3), i.e. to the reference's BSplineTrajectory; so is every lap downstream.
+ *     One dependent chain of ~5 M rotations per line (one lane per line).
+ *   STO_FIT_BLOCKS: a group of up to 32 lanes shares each line - 32 blocks of rows eliminated with their interface
+ *     unknowns symbolic, the interface system by parallel cyclic reduction over __shfl_sync, one division per row;
+ *     2-15 x faster, coefficients equal to FITPACK's up to rounding (1e-15 relative; identical for every lane count).
+ *   STO_FIT_THOMAS: one-lane Thomas + Sherman-Morrison recurrences (same accuracy class as BLOCKS).
+ * The reference's QSS is a discontinuous function of its inputs: with the two approximate solvers 1-2 lines in 500
+ * land on the other side of a stop / overwrite decision and their laps move by 1e-6 .. 1e-4 s. */
+enum { STO_FIT_THOMAS = 0, STO_FIT_BLOCKS = 1, STO_FIT_FITPACK = 2 };
+int sto_set_fit_solver(int solver);          /* process-wide; returns STO_ERR_INVALID for an unknown value */
+int sto_get_fit_solver(void);
+int sto_fit_solver_lanes(int M, int B);      /* lanes per candidate the selected solver's kernel uses for this size */
 int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, const double* normal_x,
                                const double* normal_y, const double* offsets, const double* px,
                                const double* py, int M, int B, int ld, double* u, double* cx, double* cy,
@@ -222,6 +230,12 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
  * best_lap[0], best_idx[0] (device).  Ties resolve to the lowest index. */
 int sto_argmin_f64(const double* lap, const int32_t* status, int B, double* best_lap, int64_t* best_idx,
                    void* stream);
+
+/* Self-test of the branch-free IEEE division / square root used by the FITPACK solver's rotation chain
+ * (csrc/sto_common.cuh): 2^27 operations on operands of every kind (all bit patterns, mid-range magnitudes of both signs,
+ * exact zeros, near-equal pairs).  mismatches = results that differ from the plain `/` and sqrt() while the range flag
+ * was down (must be 0); flagged = operations outside the fast path's range (the kernels redo those with the operators). */
+int sto_selftest_fp64(unsigned long long seed, long long* tested, long long* mismatches, long long* flagged);
 
 /* FP64 pipe peak of the current device in TFLOP/s (2 flops per DFMA; 8 independent chains per thread, every SM full;
  * best of 3 timed launches, synchronous): the denominator of bench.py's FP64 utilisation figure. */

@@ -93,9 +93,10 @@ def maxlat(veh, lon, ref_pow=1):
 
 
 def set_fit_solver(name):
-    """'blocks' (default): 32-block elimination + cyclic reduction, the CUDA library's default solver; 'thomas': one-lane
-    Thomas + Sherman-Morrison (library: sto_set_fit_partition(0)).  Applies to fit_periodic_cubic and lap_batch."""
-    lib().sto_oracle_set_fit_solver({"blocks": 1, "thomas": 0}[name])
+    """'fitpack' (default): FITPACK's fpclos Givens sweep, bit-identical to scipy splprep(per=1, s=0) = the reference;
+    'blocks': 32-block elimination + cyclic reduction; 'thomas': one-lane Thomas + Sherman-Morrison.  The CUDA library
+    has the same three (sto_set_fit_solver).  Applies to fit_periodic_cubic and lap_batch."""
+    lib().sto_oracle_set_fit_solver({"fitpack": 2, "blocks": 1, "thomas": 0}[name])
 
 
 def fit_periodic_cubic(points):

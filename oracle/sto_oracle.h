@@ -24,7 +24,8 @@ typedef struct sto_oracle_vehicle {
 
 double sto_oracle_ppoly(const double* x, const double* c, int n_break, int order, double v);
 double sto_oracle_maxlat(const sto_oracle_vehicle* V, double lon, int ref_pow);
-/* solver of the cyclic collocation system: 1 (default) block elimination + cyclic reduction, 0 Thomas + Sherman-Morrison */
+/* solver of the interpolation system: 2 (default) FITPACK's fpclos Givens sweep (the reference's arithmetic, bit for bit),
+ * 1 block elimination + cyclic reduction, 0 Thomas + Sherman-Morrison */
 void sto_oracle_set_fit_solver(int solver);
 int sto_oracle_fit_periodic_cubic(const double* px, const double* py, int M, double* t, double* cx,
                                   double* cy);

@@ -60,14 +60,17 @@ _SIGNATURES = {
     "sto_fit_periodic_lsq_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [_vp, C.c_int, C.c_int] + [_vp] * 5 +
                                  [C.c_size_t, _vp]),
     "sto_set_stage_timing": (C.c_int, [C.c_int]),
-    "sto_set_fit_partition": (None, [C.c_int]),
-    "sto_fit_partition_lanes": (C.c_int, [C.c_int, C.c_int]),
+    "sto_set_fit_solver": (C.c_int, [C.c_int]),
+    "sto_get_fit_solver": (C.c_int, []),
+    "sto_fit_solver_lanes": (C.c_int, [C.c_int, C.c_int]),
     "sto_last_stage_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "sto_selftest_fp64": (C.c_int, [C.c_ulonglong] + [C.POINTER(C.c_longlong)] * 3),
     "sto_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
     "sto_argmin_f64": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "sto_transpose_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+FIT_THOMAS, FIT_BLOCKS, FIT_FITPACK = 0, 1, 2   # sto_set_fit_solver
 
 _lib = None
 

@@ -56,28 +56,34 @@ int pick_fit_split(int B) {
     if (B <= 65536) return 2;
     return 1;
 }
-// The cyclic solve of the fit: by default a group of lanes shares each candidate (sto_fit.cuh, "partitioned cyclic
-// solve": block elimination per lane + PCR over warp shuffles, one division per row); mode 0 selects the one-lane
-// Thomas + Sherman-Morrison recurrences (bit-identical to oracle/sto_oracle.c's solver).  g_fit_part: -1 / 1 partitioned,
-// 0 Thomas.  Lanes per candidate measured on B200 (tools/fit_part_bench.py, ms at M = 2895 | 23,160):
-//   B =   256: Thomas x8 2.7 | 30.7   partitioned x32 0.27 |  2.7
-//   B =  1024: Thomas x8 3.6 | 32.8   partitioned x16 0.64 |  7.7   (x32 0.58 | 11.3)
-//   B =  4096: Thomas x8 4.2 | 34.3   partitioned x8  1.81 | 16.1
-//   B = 16384: Thomas x1 8.8 | 71.2   partitioned x4  3.60 | 29.8
-//   B = 32768: Thomas x2 8.7          partitioned x2  5.9          B = 65536: Thomas x1 11.4, partitioned x1 9.2
-int g_fit_part = -1;
-struct FitPlan { int split; bool part; };
+// Solver of the fit's interpolation system (include/sto_b200.h, sto_set_fit_solver):
+//   STO_FIT_FITPACK (default)  FITPACK's own Givens sweep, restated operation by operation (sto_fit.cuh): coefficients
+//                              bit-identical to the reference's scipy splprep, one dependent chain per line;
+//   STO_FIT_BLOCKS             a group of lanes shares each line: 32-block elimination + PCR over warp shuffles, one
+//                              division per row; coefficients equal up to rounding (1e-15);
+//   STO_FIT_THOMAS             one-lane Thomas + Sherman-Morrison recurrences (same accuracy class as BLOCKS).
+// Lanes per candidate of the BLOCKS solver measured on B200 (tools/fit_part_bench.py, ms at M = 2895 | 23,160):
+//   B =   256: Thomas x8 2.7 | 30.7   blocks x32 0.27 |  2.7
+//   B =  1024: Thomas x8 3.6 | 32.8   blocks x16 0.64 |  7.7   (x32 0.58 | 11.3)
+//   B =  4096: Thomas x8 4.2 | 34.3   blocks x8  1.81 | 16.1
+//   B = 16384: Thomas x1 8.8 | 71.2   blocks x4  3.60 | 29.8
+//   B = 32768: Thomas x2 8.7          blocks x2  5.9          B = 65536: Thomas x1 11.4, blocks x1 9.2
+int g_fit_solver = STO_FIT_FITPACK;
+struct FitPlan { int split; int solver; };
 FitPlan pick_fit_plan(int M, int B) {
-    int mode = g_fit_part;
-    if (const char* e = getenv("STO_FIT_PART")) mode = atoi(e);
-    if (mode == 0) return FitPlan{pick_fit_split(B), false};
+    int solver = g_fit_solver;
+    if (const char* e = getenv("STO_FIT_SOLVER")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) solver = v;
+    }
+    if (solver != STO_FIT_BLOCKS) return FitPlan{pick_fit_split(B), solver};
     int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 24576) ? 4 : (B <= 49152) ? 2 : 1;
     if (const char* e = getenv("STO_FIT_SPLIT")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
     }
     if (M < 256) lanes = 1;   // one block (sto::fit_part_blocks): nothing to share
-    return FitPlan{lanes, true};
+    return FitPlan{lanes, STO_FIT_BLOCKS};
 }
 
 // Lanes per candidate for kernels whose samples are independent: fill ~8 warps per SM before going one-per-candidate.
@@ -104,13 +110,14 @@ struct Carver {
 
 inline size_t ldof(int B) { return (size_t)((B + 31) & ~31); }  // internal leading dimension
 
-struct FitWork { double *cp, *zx, *zy, *zz; };
+struct FitWork { double *cp, *zx, *zy, *zz, *ze; };
 FitWork carve_fit(Carver& c, int M, size_t ld) {
     FitWork w;
     w.cp = c.take<double>((size_t)M * ld);
     w.zx = c.take<double>((size_t)M * ld);
     w.zy = c.take<double>((size_t)M * ld);
     w.zz = c.take<double>((size_t)M * ld);
+    w.ze = c.take<double>((size_t)M * ld);
     return w;
 }
 
@@ -169,7 +176,8 @@ void launch_fit(const sto::FitArgs& A, const FitPlan& plan, cudaStream_t st) {
     const int split = plan.split;
     const int block = pick_block(A.B * split);
     const int grid = grid_for(A.B * split, block);
-    if (!plan.part) { fit_kernel<0><<<grid, block, 0, st>>>(A, split); return; }
+    if (plan.solver == STO_FIT_THOMAS) { fit_kernel<0><<<grid, block, 0, st>>>(A, split); return; }
+    if (plan.solver == STO_FIT_FITPACK) { fit_kernel<-1><<<grid, block, 0, st>>>(A, split); return; }
     switch (32 / split) {   // blocks per lane (one block in all when M < 256: plan.split == 1, any instantiation)
         case 1: fit_kernel<1><<<grid, block, 0, st>>>(A, split); break;
         case 2: fit_kernel<2><<<grid, block, 0, st>>>(A, split); break;
@@ -295,6 +303,51 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     }
     const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (r == 123.456) out[0] = r;   // never true: keeps the chains alive
+}
+
+// Self-test of the flagged fast-path division / square root (sto_common.cuh): every thread draws operand pairs from a
+// counter-based generator - all bit patterns, mid-range magnitudes, near-equal pairs, exact zeros - and counts results
+// that differ from the plain operators while the flag is down, and how often the flag is up.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__global__ void fp64_selftest_kernel(unsigned long long seed, int per_thread, unsigned long long* counts) {
+#if defined(__CUDA_ARCH__)
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = 0, flagged = 0;
+    for (int i = 0; i < per_thread; ++i) {
+        const unsigned long long r0 = splitmix64(seed + (tid * (unsigned long long)per_thread + i) * 3ull);
+        const unsigned long long r1 = splitmix64(r0), r2 = splitmix64(r1);
+        double a, b;
+        const int mode = (int)(r2 & 7);
+        if (mode < 3) {            // any bit pattern: all exponents, signs, NaN / inf / denormals
+            a = __longlong_as_double((long long)r0);
+            b = __longlong_as_double((long long)r1);
+        } else if (mode < 6) {     // mid-range magnitudes, both signs
+            a = (double)(r0 >> 11) * (1.0 / 9007199254740992.0) * 2e6 - 1e6;
+            b = exp2((double)((int)(r1 >> 58) - 32)) * (1.0 + (double)(r1 & 0xfffffffffffffull) * (1.0 / 4503599627370496.0));
+            if (r2 & 8) b = -b;
+        } else {                   // near-equal operands, exact zeros
+            a = (double)(r0 >> 11) * (1.0 / 9007199254740992.0) * 100.0;
+            b = ((r1 & 3) == 0) ? a : a + (double)((long long)(r1 >> 60) - 8) * 1e-12;
+            if ((r1 & 12) == 0) a = (r1 & 16) ? 0.0 : -0.0;
+            if (r2 & 8) b = -b;
+        }
+        bool s1 = false, s2 = false;
+        const double q = sto::div_fast(a, b, s1);
+        const double qr = a / b;
+        const double sa = fabs(a);
+        const double w = sto::sqrt_fast(sa, s2);
+        const double wr = sqrt(sa);
+        if (s1) ++flagged; else if (__double_as_longlong(q) != __double_as_longlong(qr) && !(q != q && qr != qr)) ++bad;
+        if (s2) ++flagged; else if (__double_as_longlong(w) != __double_as_longlong(wr) && !(w != w && wr != wr)) ++bad;
+    }
+    atomicAdd(&counts[0], bad);
+    atomicAdd(&counts[1], flagged);
+#endif
 }
 
 __global__ void zero_status_kernel(int32_t* s, int B) {
@@ -485,11 +538,16 @@ extern "C" {
 int sto_abi_version(void) { return STO_B200_ABI_VERSION; }
 const char* sto_last_error(void) { return g_err.c_str(); }
 
-void sto_set_fit_partition(int mode) { g_fit_part = (mode < 0) ? -1 : (mode > 0 ? 1 : 0); }
-int sto_fit_partition_lanes(int M, int B) {
+int sto_set_fit_solver(int solver) {
+    if (solver != STO_FIT_THOMAS && solver != STO_FIT_BLOCKS && solver != STO_FIT_FITPACK)
+        return fail(STO_ERR_INVALID, "unknown fit solver");
+    g_fit_solver = solver;
+    return STO_OK;
+}
+int sto_get_fit_solver(void) { return g_fit_solver; }
+int sto_fit_solver_lanes(int M, int B) {
     if (M < 3 || B < 1) return 0;
-    const FitPlan p = pick_fit_plan(M, B);
-    return p.part ? p.split : 0;
+    return pick_fit_plan(M, B).split;
 }
 
 int sto_device_count(void) {
@@ -528,6 +586,7 @@ int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, c
     A.zx = c.take<double>((size_t)M * ld);
     A.zy = c.take<double>((size_t)M * ld);
     A.zz = c.take<double>((size_t)M * ld);
+    A.ze = c.take<double>((size_t)M * ld);
     if (c.bytes() > work_bytes && (size_t)ld > ldof(B)) return fail(STO_ERR_WORKSPACE, "fit workspace: ld too large");
     if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "fit workspace too small");
     A.cenx = centre_x; A.ceny = centre_y; A.nrmx = normal_x; A.nrmy = normal_y; A.off = offsets;
@@ -727,7 +786,7 @@ int sto_lap_time_f64(const double* centre_x, const double* centre_y, const doubl
     sto::FitArgs F{};
     F.cenx = centre_x; F.ceny = centre_y; F.nrmx = normal_x; F.nrmy = normal_y; F.off = offsets;
     F.M = M; F.B = B; F.ld = ld; F.u = w.u; F.cx = w.cx; F.cy = w.cy; F.status = status;
-    F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz;
+    F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz; F.ze = w.fit.ze;
     {
         launch_fit(F, pick_fit_plan(M, B), st);
     }
@@ -805,6 +864,22 @@ int sto_transpose_f64(const double* src, int rows, int cols, int ld_src, double*
     dim3 g((cols + 31) / 32, (rows + 31) / 32), blk(32, 8);
     transpose_kernel<<<g, blk, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, ld_src, dst, ld_dst);
     STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_selftest_fp64(unsigned long long seed, long long* tested, long long* mismatches, long long* flagged) {
+    if (!tested || !mismatches || !flagged) return fail(STO_ERR_INVALID, "NULL argument");
+    unsigned long long* counts = nullptr;
+    STO_CUDA(cudaMalloc(&counts, 2 * sizeof(unsigned long long)));
+    STO_CUDA(cudaMemset(counts, 0, 2 * sizeof(unsigned long long)));
+    const int block = 256, grid = 1024, per_thread = 256;   // 2^26 operand pairs, two operations each
+    fp64_selftest_kernel<<<grid, block>>>(seed, per_thread, counts);
+    unsigned long long h[2] = {0, 0};
+    STO_CUDA(cudaMemcpy(h, counts, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(counts);
+    *tested = 2LL * block * grid * per_thread;
+    *mismatches = (long long)h[0];
+    *flagged = (long long)h[1];
     return STO_OK;
 }
 

@@ -25,7 +25,7 @@ struct FitArgs {
     int M, B, ld;
     double *u, *cx, *cy;                        // outputs: [M+1][ld], [M+3][ld], [M+3][ld]
     int32_t* status;                            // [B] (may be NULL)
-    double *cp, *zx, *zy, *zz;                  // work: [M][ld] each
+    double *cp, *zx, *zy, *zz, *ze;             // work: [M][ld] each (ze: the FITPACK solver only)
 };
 
 STO_HD void fit_point(const FitArgs& A, int i, int b, double& x, double& y) {
@@ -660,6 +660,314 @@ STO_HD void fit_solve_partitioned_emulated(const FitArgs& A, int b, int P) {
     }
 }
 
+// ---- FITPACK's own arithmetic: fpclos for s = 0, k = 3 (the reference's fit, bit for bit) ---------------------------
+// BSplineTrajectory.__init__ (models/trajectory.py:219-220) is scipy.interpolate.splprep(per=True) = FITPACK clocur ->
+// fpclos (Dierckx; SciPy 1.18.1, un-vendored).  For an interpolating closed cubic, fpclos puts a knot at every data
+// parameter, evaluates the three non-zero B-splines of every point with fpbspl (de Boor-Cox recurrence), rotates the
+// M observation rows one by one into an upper triangular band matrix a1 (bandwidth 3) with Givens rotations WITHOUT
+// square-root-free tricks (fpgivs / fprota), carries the last two columns - which the periodicity condition couples to
+// the first rows - in a dense M x 2 block a2, rotates the last two rows through ALL of a1 (the periodic wrap), and
+// back-substitutes (fpbacp).  This is a restatement of that published algorithm, operation by operation, from the
+// FITPACK routines' documented structure; scipy's coefficients are reproduced bit for bit on every golden line and on
+// 4,096 bench lines (tests/), so laps downstream equal the reference's to the last bit as well.
+// The sweep is one dependent chain of ~5 M rotations per line (one lane per line); only the B-spline values are
+// computed ahead by all lanes of the group.
+struct FpRot { double c, s; };
+STO_HD FpRot fp_givs(double piv, double& ww) {           // fpgivs: dd = sqrt(piv^2 + ww^2) without overflow
+    // if (store >= ww) dd = store * sqrt(1 + (ww / piv)^2) else dd = ww * sqrt(1 + (piv / ww)^2): the same operations
+    // on selected operands, so the lanes of a warp (different lines) do not diverge
+    const double store = fabs(piv);
+    const bool big = store >= ww;
+    const double num = big ? ww : piv, den = big ? piv : ww, base = big ? store : ww;
+    FpRot g;
+#if defined(__CUDA_ARCH__) && !defined(STO_NO_FAST_FP64)
+    {   // straight-line copy of the operators' fast paths (sto_common.cuh): cos and sin overlap; redone below if flagged
+        bool slow = false;
+        const double r = div_fast(num, den, slow);
+        const double dd = base * sqrt_fast(1.0 + r * r, slow);
+        g.c = div_fast(ww, dd, slow);
+        g.s = div_fast(piv, dd, slow);
+        if (!slow) { ww = dd; return g; }
+    }
+#endif
+    const double r = num / den;
+    const double dd = base * sqrt(1.0 + r * r);
+    g.c = ww / dd;
+    g.s = piv / dd;
+    ww = dd;
+    return g;
+}
+STO_HD void fp_rota(const FpRot& g, double& a, double& b) {   // fprota
+    const double s1 = a, s2 = b;
+    b = g.c * s2 + g.s * s1;
+    a = g.c * s1 - g.s * s2;
+}
+
+// fpbspl at a knot: the (k + 1 = 4) B-spline values at x = t(l) for row i (0-based), l = i + 4; the fourth is 0.
+// Results go to the slots where row i of a1 will be stored once the row has been rotated in.
+STO_HD void fit_phase_bspl_rows(const FitArgs& A, int b, int g, int G) {
+    const int M = A.M, ld = A.ld;
+    const int per = (M + G - 1) / G;
+    const int i0 = g * per, i1 = (i0 + per < M) ? i0 + per : M;
+    for (int i = i0; i < i1; ++i) {
+        double t[7];   // t[m] = t(l - 3 + m), m = 0..6 (1-based FITPACK knot index l = i + 4)
+#pragma unroll
+        for (int m = 0; m < 7; ++m) t[m] = fit_knot(A, i - 3 + m, b);
+        const double x = t[3];
+        double h[5], hh[4];
+        h[0] = 1.0;
+#pragma unroll
+        for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+            for (int m = 0; m < j; ++m) hh[m] = h[m];
+            h[0] = 0.0;
+#pragma unroll
+            for (int m = 1; m <= j; ++m) {
+                const double tli = t[3 + m], tlj = t[3 + m - j];
+                if (tli == tlj) { h[m] = 0.0; continue; }
+                const double f = hh[m - 1] / (tli - tlj);
+                h[m - 1] = h[m - 1] + f * (tli - x);
+                h[m] = f * (x - tlj);
+            }
+        }
+        A.cp[at(i, ld, b)] = h[0];
+        A.zx[at(i, ld, b)] = h[1];
+        A.zy[at(i, ld, b)] = h[2];
+    }
+}
+
+#ifndef STO_FP_CHUNK
+#define STO_FP_CHUNK 4   // rows fetched ahead of the rotation chain (global round trips off the critical path)
+#endif
+
+// One periodic row on its way through the band (fpclos labels 160-240): h1(1..3) = (ha, hb, hc), h2(1..2) = (g1, g2).
+struct FpWrapRow { double ha, hb, hc, g1, g2, x, y; };
+
+// fpclos "rotation with the rows 1,2,...n10 of matrix a", one row jj (1-based) held in registers by the caller.
+STO_HD void fp_wrap_step(FpWrapRow& r, int jj, int n10, double& a1, double& a2, double& a3, double& b1, double& b2,
+                         double& zx, double& zy) {
+    const int kk = 2;
+    const double piv = r.ha;
+    if (piv == 0.0) { r.ha = r.hb; r.hb = r.hc; r.hc = 0.0; return; }
+    const FpRot g = fp_givs(piv, a1);
+    fp_rota(g, r.x, zx); fp_rota(g, r.y, zy);
+    fp_rota(g, r.g1, b1); fp_rota(g, r.g2, b2);
+    if (jj == n10) return;
+    const int i2 = (n10 - jj < kk) ? n10 - jj : kk;
+    if (i2 >= 1) { fp_rota(g, r.hb, a2); r.ha = r.hb; }
+    if (i2 >= 2) { fp_rota(g, r.hc, a3); r.hb = r.hc; }
+    if (i2 >= 2) r.hc = 0.0; else r.hb = 0.0;   // h1(i2 + 1) = 0
+}
+
+STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
+    const int M = A.M, ld = A.ld;
+    const int n7 = M, kk = 2, n10 = n7 - kk;   // kk1 = 3
+    double* const a11 = A.cp; double* const a12 = A.zx; double* const a13 = A.zy;   // a1(j, 1..3), rows 0-based
+    double* const a21 = A.zz; double* const a22 = A.ze;                            // a2(j, 1..2)
+    double* const z1 = A.cx; double* const z2 = A.cy;                              // right-hand sides, then c in place
+    // B-spline values of the two periodic rows (their slots are overwritten at the end of the regular sweep)
+    double hp[2][3];
+    for (int r = 0; r < 2; ++r) {
+        const int i = M - 2 + r;
+        hp[r][0] = a11[at(i, ld, b)]; hp[r][1] = a12[at(i, ld, b)]; hp[r][2] = a13[at(i, ld, b)];
+    }
+    // ---- rows 1 .. M-2: rotate into a1 (three rows of a1 and z live in registers; row `it` is final afterwards) ------
+    double w1[3] = {0.0, 0.0, 0.0}, w2[3] = {0.0, 0.0, 0.0}, w3[3] = {0.0, 0.0, 0.0};
+    double q1[2] = {0.0, 0.0}, q2[2] = {0.0, 0.0}, q3[2] = {0.0, 0.0};
+    for (int i0 = 0; i0 < M - 2; i0 += STO_FP_CHUNK) {
+        double hs[STO_FP_CHUNK][3], ps[STO_FP_CHUNK][2];
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int i = i0 + c;
+            hs[c][0] = hs[c][1] = hs[c][2] = ps[c][0] = ps[c][1] = 0.0;
+            if (i < M - 2) {
+                hs[c][0] = a11[at(i, ld, b)]; hs[c][1] = a12[at(i, ld, b)]; hs[c][2] = a13[at(i, ld, b)];
+                fit_point(A, i, b, ps[c][0], ps[c][1]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int i = i0 + c;
+            if (i >= M - 2) break;
+            double h1 = hs[c][0], h2 = hs[c][1], h3 = hs[c][2];
+            double xi = ps[c][0], yi = ps[c][1];
+            if (h1 != 0.0) {
+                const FpRot g = fp_givs(h1, w1[0]);
+                fp_rota(g, xi, q1[0]); fp_rota(g, yi, q1[1]);
+                fp_rota(g, h2, w1[1]); fp_rota(g, h3, w1[2]);
+            }
+            if (h2 != 0.0) {
+                const FpRot g = fp_givs(h2, w2[0]);
+                fp_rota(g, xi, q2[0]); fp_rota(g, yi, q2[1]);
+                fp_rota(g, h3, w2[1]);
+            }
+            if (h3 != 0.0) {
+                // band row i + 2 is untouched so far (all zero): fpgivs gives dd = |h3| * sqrt(1 + (0 / h3)^2) = |h3|,
+                // cos = 0 / dd = 0, sin = h3 / dd = 1 (B-spline values are >= 0), and fprota leaves
+                // z = 0 * 0 + 1 * x = 0 + x - the rotation costs nothing, bit for bit
+                w3[0] = fabs(h3);
+                q3[0] = 0.0 + xi; q3[1] = 0.0 + yi;
+            }
+            a11[at(i, ld, b)] = w1[0]; a12[at(i, ld, b)] = w1[1]; a13[at(i, ld, b)] = w1[2];
+            z1[at(i, ld, b)] = q1[0]; z2[at(i, ld, b)] = q1[1];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { w1[k] = w2[k]; w2[k] = w3[k]; w3[k] = 0.0; }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { q1[k] = q2[k]; q2[k] = q3[k]; q3[k] = 0.0; }
+        }
+    }
+    // the window now holds rows M-2 and M-1 (0-based) of a1 / z
+    a11[at(M - 2, ld, b)] = w1[0]; a12[at(M - 2, ld, b)] = w1[1]; a13[at(M - 2, ld, b)] = w1[2];
+    z1[at(M - 2, ld, b)] = q1[0]; z2[at(M - 2, ld, b)] = q1[1];
+    a11[at(M - 1, ld, b)] = w2[0]; a12[at(M - 1, ld, b)] = w2[1]; a13[at(M - 1, ld, b)] = w2[2];
+    z1[at(M - 1, ld, b)] = q2[0]; z2[at(M - 1, ld, b)] = q2[1];
+    // ---- a2: the last two columns of the band, as a dense M x 2 block (zero except six entries; the zeros of rows
+    //      1 .. n10 are supplied on the fly below, where those rows are first touched) ---------------------------------
+    double init21[3] = {0.0, 0.0, 0.0}, init22[3] = {0.0, 0.0, 0.0};   // a2(n10 - 1 + k, 1..2), k = 0..2 (rows M-3 .. M-1, 0-based)
+    {
+        int jk = n10 + 1;                      // 1-based as in fpclos
+        for (int i = 1; i <= kk; ++i) {
+            int ik = jk;
+            for (int j = 1; j <= 3; ++j) {
+                if (ik <= 0) break;
+                const double v = (j == 1 ? a11 : j == 2 ? a12 : a13)[at(ik - 1, ld, b)];
+                const int slot = ik - (n10 - 1);      // rows n10-1 .. n10+2 (1-based) -> 0..3
+                if (slot >= 0 && slot < 3) { if (i == 1) init21[slot] = v; else init22[slot] = v; }
+                else if (slot == 3) { if (i == 1) a21[at(ik - 1, ld, b)] = v; else a22[at(ik - 1, ld, b)] = v; }
+                --ik;
+            }
+            ++jk;
+        }
+        // rows n10+1, n10+2 (1-based) hold the border block: written here; row n10+2 = M only gets a2(M, 2)
+        a21[at(M - 1, ld, b)] = 0.0;
+        a21[at(M - 2, ld, b)] = init21[2]; a22[at(M - 2, ld, b)] = init22[2];
+        if (kk >= 2) { /* a22(M) was stored through slot == 3 above */ }
+    }
+    // ---- rows M-1 and M: the periodicity condition couples them to the first columns.  Both rows travel through the
+    //      band together: row M-1 rotates against band row jj, then row M against the updated band row (exactly the
+    //      order of two successive sweeps, since neither revisits a band row) ----------------------------------------
+    FpWrapRow wr[2];
+    for (int r = 0; r < 2; ++r) {
+        const int it = M - 1 + r;              // 1-based row number
+        const int l5 = it - 1;
+        const double h[4] = {0.0, hp[r][0], hp[r][1], hp[r][2]};
+        double h1[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, h2[4] = {0.0, 0.0, 0.0, 0.0};
+        fit_point(A, it - 1, b, wr[r].x, wr[r].y);
+        int j = l5 - n10;
+        for (int i = 1; i <= 3; ++i) {
+            ++j;
+            int l0 = j;
+            for (;;) {
+                const int l1 = l0 - kk;
+                if (l1 <= 0) { h2[l0] = h2[l0] + h[i]; break; }
+                if (l1 <= n10) { h1[l1] = h[i]; break; }
+                l0 = l1 - n10;
+            }
+        }
+        wr[r].ha = h1[1]; wr[r].hb = h1[2]; wr[r].hc = h1[3]; wr[r].g1 = h2[1]; wr[r].g2 = h2[2];
+    }
+    for (int j0 = 1; j0 <= n10; j0 += STO_FP_CHUNK) {
+        double ra1[STO_FP_CHUNK], ra2[STO_FP_CHUNK], ra3[STO_FP_CHUNK], rzx[STO_FP_CHUNK], rzy[STO_FP_CHUNK];
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int jj = j0 + c;
+            ra1[c] = ra2[c] = ra3[c] = rzx[c] = rzy[c] = 0.0;
+            if (jj <= n10) {
+                ra1[c] = a11[at(jj - 1, ld, b)]; ra2[c] = a12[at(jj - 1, ld, b)]; ra3[c] = a13[at(jj - 1, ld, b)];
+                rzx[c] = z1[at(jj - 1, ld, b)]; rzy[c] = z2[at(jj - 1, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int jj = j0 + c;
+            if (jj > n10) break;
+            const int slot = jj - (n10 - 1);   // the two band rows that already carry a2 entries
+            double b1 = (slot >= 0) ? init21[slot] : 0.0, b2 = (slot >= 0) ? init22[slot] : 0.0;
+            fp_wrap_step(wr[0], jj, n10, ra1[c], ra2[c], ra3[c], b1, b2, rzx[c], rzy[c]);
+            fp_wrap_step(wr[1], jj, n10, ra1[c], ra2[c], ra3[c], b1, b2, rzx[c], rzy[c]);
+            a11[at(jj - 1, ld, b)] = ra1[c]; a12[at(jj - 1, ld, b)] = ra2[c]; a13[at(jj - 1, ld, b)] = ra3[c];
+            z1[at(jj - 1, ld, b)] = rzx[c]; z2[at(jj - 1, ld, b)] = rzy[c];
+            a21[at(jj - 1, ld, b)] = b1; a22[at(jj - 1, ld, b)] = b2;
+        }
+    }
+    for (int r = 0; r < 2; ++r) {              // rotation with rows n10+1 .. n7 of a2 (row M-1 completely, then row M)
+        double gg[3] = {0.0, wr[r].g1, wr[r].g2};
+        for (int jj = 1; jj <= kk; ++jj) {
+            const int ij = n10 + jj;
+            if (ij <= 0) continue;
+            const double piv = gg[jj];
+            if (piv == 0.0) continue;
+            double* const col = (jj == 1) ? a21 : a22;
+            double ww = col[at(ij - 1, ld, b)];
+            const FpRot g = fp_givs(piv, ww);
+            col[at(ij - 1, ld, b)] = ww;
+            double zz1 = z1[at(ij - 1, ld, b)], zz2 = z2[at(ij - 1, ld, b)];
+            fp_rota(g, wr[r].x, zz1); fp_rota(g, wr[r].y, zz2);
+            z1[at(ij - 1, ld, b)] = zz1; z2[at(ij - 1, ld, b)] = zz2;
+            if (jj == kk) break;
+            double v = a22[at(ij - 1, ld, b)];
+            fp_rota(g, gg[2], v);
+            a22[at(ij - 1, ld, b)] = v;
+        }
+    }
+    // ---- fpbacp: back substitution, c in place of z -----------------------------------------------------------------
+    const int n = n7, n2 = n - kk;
+    double cn1x, cn1y, cn2x, cn2y;            // c(n2+1), c(n2+2) = the two border unknowns
+    {
+        cn2x = z1[at(n - 1, ld, b)] / a22[at(n - 1, ld, b)];
+        cn2y = z2[at(n - 1, ld, b)] / a22[at(n - 1, ld, b)];
+        double sx = z1[at(n - 2, ld, b)], sy = z2[at(n - 2, ld, b)];
+        sx = sx - cn2x * a22[at(n - 2, ld, b)];
+        sy = sy - cn2y * a22[at(n - 2, ld, b)];
+        cn1x = sx / a21[at(n - 2, ld, b)];
+        cn1y = sy / a21[at(n - 2, ld, b)];
+        z1[at(n - 1, ld, b)] = cn2x; z2[at(n - 1, ld, b)] = cn2y;
+        z1[at(n - 2, ld, b)] = cn1x; z2[at(n - 2, ld, b)] = cn1y;
+    }
+    double px1 = 0.0, py1 = 0.0, px2 = 0.0, py2 = 0.0;   // c(i+1), c(i+2) of the band part
+    for (int i0 = n2; i0 >= 1; i0 -= STO_FP_CHUNK) {
+        double ra1[STO_FP_CHUNK], ra2[STO_FP_CHUNK], ra3[STO_FP_CHUNK], rb1[STO_FP_CHUNK], rb2[STO_FP_CHUNK],
+               rzx[STO_FP_CHUNK], rzy[STO_FP_CHUNK];
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int i = i0 - c;
+            ra1[c] = 1.0; ra2[c] = ra3[c] = rb1[c] = rb2[c] = rzx[c] = rzy[c] = 0.0;
+            if (i >= 1) {
+                ra1[c] = a11[at(i - 1, ld, b)]; ra2[c] = a12[at(i - 1, ld, b)]; ra3[c] = a13[at(i - 1, ld, b)];
+                rb1[c] = a21[at(i - 1, ld, b)]; rb2[c] = a22[at(i - 1, ld, b)];
+                rzx[c] = z1[at(i - 1, ld, b)]; rzy[c] = z2[at(i - 1, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int i = i0 - c;
+            if (i < 1) break;
+            double sx = rzx[c], sy = rzy[c];
+            sx = sx - cn1x * rb1[c]; sx = sx - cn2x * rb2[c];
+            sy = sy - cn1y * rb1[c]; sy = sy - cn2y * rb2[c];
+            const int jb = n2 - i + 1;         // fpbacp's j: 1 for the last band row
+            const int i1 = (jb <= kk) ? jb - 1 : kk;
+            if (i1 >= 1) { sx = sx - px1 * ra2[c]; sy = sy - py1 * ra2[c]; }
+            if (i1 >= 2) { sx = sx - px2 * ra3[c]; sy = sy - py2 * ra3[c]; }
+#if defined(__CUDA_ARCH__) && !defined(STO_NO_FAST_FP64)
+            {
+                bool slow = false;
+                const double qx = div_fast(sx, ra1[c], slow), qy = div_fast(sy, ra1[c], slow);
+                if (slow) { sx = sx / ra1[c]; sy = sy / ra1[c]; } else { sx = qx; sy = qy; }
+            }
+#else
+            sx = sx / ra1[c]; sy = sy / ra1[c];
+#endif
+            z1[at(i - 1, ld, b)] = sx; z2[at(i - 1, ld, b)] = sy;
+            px2 = px1; py2 = py1; px1 = sx; py1 = sy;
+        }
+    }
+    for (int i = 0; i < 3; ++i) {              // c(n7 + i) = c(i)
+        z1[at(M + i, ld, b)] = z1[at(i, ld, b)];
+        z2[at(M + i, ld, b)] = z2[at(i, ld, b)];
+    }
+}
+
 STO_HD void fit_degenerate(const FitArgs& A, int b) {  // FITPACK returns ier=10; scipy raises
     const int M = A.M, ld = A.ld;
     if (A.status) A.status[b] |= STO_CAND_DEGENERATE_FIT;
@@ -669,7 +977,8 @@ STO_HD void fit_degenerate(const FitArgs& A, int b) {  // FITPACK returns ier=10
 }
 
 // One lane of a group of G (device).  Lanes 0..2 run the three recurrences when G >= 3.
-// PART_E = 0: Thomas recurrences; PART_E > 0: partitioned solve with PART_E blocks per lane (device only).
+// PART_E = 0: Thomas recurrences; PART_E > 0: partitioned solve with PART_E blocks per lane (device only);
+// PART_E < 0: FITPACK's Givens sweep (one lane per line; the other lanes of the group help with the row phases).
 template <int PART_E = 0>
 STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int G, int lane0) {
     (void)lane0;
@@ -687,6 +996,12 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
     if (active && !ok) { if (g == 0) fit_degenerate(A, b); }
     if (active && ok) fit_phase_normalise(A, b, g, G, total);
     STO_FIT_SYNC();
+    if (PART_E < 0) {
+        if (active && ok) fit_phase_bspl_rows(A, b, g, G);
+        STO_FIT_SYNC();
+        if (active && ok && g == 0) fit_solve_fitpack(A, b);
+        return;
+    }
     if (active && ok) fit_phase_rows(A, b, g, G);
     STO_FIT_SYNC();
 #if defined(__CUDA_ARCH__)
@@ -713,11 +1028,16 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
 
 // Whole fit by one caller: G = 1 is the plain one-lane fit; G > 1 plays the lanes of a group one after another (host
 // emulation of the device schedule, used by the tests).
-STO_HD void fit_candidate(const FitArgs& A, int b, int G = 1, bool part = false) {
+STO_HD void fit_candidate(const FitArgs& A, int b, int G = 1, bool part = false, bool fitpack = false) {
     for (int g = 0; g < G; ++g) fit_phase_segments(A, b, g, G);
     const double total = fit_phase_cumsum(A, b);
     if (!(total > 0.0)) { fit_degenerate(A, b); return; }
     for (int g = 0; g < G; ++g) fit_phase_normalise(A, b, g, G, total);
+    if (fitpack) {
+        for (int g = 0; g < G; ++g) fit_phase_bspl_rows(A, b, g, G);
+        fit_solve_fitpack(A, b);
+        return;
+    }
     for (int g = 0; g < G; ++g) fit_phase_rows(A, b, g, G);
     if (part) { fit_solve_partitioned_emulated(A, b, fit_part_blocks(A.M)); return; }
     if (G >= 3) {

@@ -229,7 +229,7 @@ class BatchedLineEvaluator:
         cy = torch.empty((M + 3, ld), dtype=torch.float64, device=dev)
         st = torch.zeros(ld, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            work = torch.empty(4 * M * ld * 8 + 4096, dtype=torch.uint8, device=dev)
+            work = torch.empty(5 * M * ld * 8 + 4096, dtype=torch.uint8, device=dev)
             if offsets_sm is not None:
                 assert M == self.M
                 args = (_ptr(self.d["cx"]), _ptr(self.d["cy"]), _ptr(self.d["nx"]), _ptr(self.d["ny"]),

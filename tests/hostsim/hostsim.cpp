@@ -21,12 +21,17 @@ extern "C" {
 int hostsim_fit(const double* cenx, const double* ceny, const double* nrmx, const double* nrmy, const double* off,
                 const double* px, const double* py, int M, int B, int ld, double* u, double* cx, double* cy,
                 int32_t* status, int split) {
-    std::vector<double> w((size_t)4 * M * ld);
+    std::vector<double> w((size_t)5 * M * ld);
     sto::FitArgs A{};
     A.cenx = cenx; A.ceny = ceny; A.nrmx = nrmx; A.nrmy = nrmy; A.off = off; A.px = px; A.py = py;
     A.M = M; A.B = B; A.ld = ld; A.u = u; A.cx = cx; A.cy = cy; A.status = status;
     A.cp = w.data(); A.zx = A.cp + (size_t)M * ld; A.zy = A.zx + (size_t)M * ld; A.zz = A.zy + (size_t)M * ld;
-    for (int b = 0; b < B; ++b) sto::fit_candidate(A, b, split < 0 ? -split : split, split < 0);   // split < 0: partitioned solve over |split| lanes
+    A.ze = A.zz + (size_t)M * ld;
+    // split > 0: Thomas; -32 <= split < 0: partitioned solve over |split| lanes; split <= -100: FITPACK's Givens sweep, |split| - 100 lanes
+    for (int b = 0; b < B; ++b) {
+        if (split <= -100) sto::fit_candidate(A, b, -split - 100 > 0 ? -split - 100 : 1, false, true);
+        else sto::fit_candidate(A, b, split < 0 ? -split : split, split < 0);
+    }
     return 0;
 }
 

@@ -33,18 +33,20 @@ def sto():
 
 @contextlib.contextmanager
 def fit_solver(name):
-    """Selects the solver of the cyclic collocation system in the library AND in the oracle, which restates both:
-    'thomas' = one-lane Thomas + Sherman-Morrison recurrences, 'partitioned' = the default (32 blocks + cyclic reduction,
-    lane groups on the device).  With matching solvers everything is bit-exact against O.lap_batch."""
+    """Selects the solver of the fit's interpolation system in the library AND in the oracle, which restates all three:
+    'fitpack' = the default, FITPACK's own Givens sweep (bit-identical to the reference's SciPy fit), 'partitioned' = 32
+    blocks + cyclic reduction (lane groups on the device), 'thomas' = one-lane Thomas + Sherman-Morrison recurrences.
+    With matching solvers everything is bit-exact against O.lap_batch."""
     from spline_trajectory_optimization_b200 import _lib
     lib = _lib.load()
-    lib.sto_set_fit_partition(0 if name == "thomas" else -1)
-    O.set_fit_solver("thomas" if name == "thomas" else "blocks")   # the oracle restates both solvers
+    code = {"thomas": _lib.FIT_THOMAS, "partitioned": _lib.FIT_BLOCKS, "fitpack": _lib.FIT_FITPACK}[name]
+    _lib.check(lib.sto_set_fit_solver(code))
+    O.set_fit_solver({"thomas": "thomas", "partitioned": "blocks", "fitpack": "fitpack"}[name])   # the oracle restates all three
     try:
         yield
     finally:
-        lib.sto_set_fit_partition(-1)
-        O.set_fit_solver("blocks")
+        _lib.check(lib.sto_set_fit_solver(_lib.FIT_FITPACK))
+        O.set_fit_solver("fitpack")
 
 
 def _evaluator(sto, d, ts=None, bank=None, impl="memo"):
@@ -56,13 +58,13 @@ def _evaluator(sto, d, ts=None, bank=None, impl="memo"):
 
 
 @pytest.mark.parametrize("name", CAND_CASES)
-@pytest.mark.parametrize("solver", ["thomas", "partitioned"])
+@pytest.mark.parametrize("solver", ["fitpack", "thomas", "partitioned"])
 def test_fit_and_sample(sto, name, solver):
     with fit_solver(solver):
-        _fit_and_sample(sto, name)
+        _fit_and_sample(sto, name, solver)
 
 
-def _fit_and_sample(sto, name):
+def _fit_and_sample(sto, name, solver):
     d = golden(name)
     ev = _evaluator(sto, d)
     B, M = d["offsets"].shape
@@ -77,6 +79,10 @@ def _fit_and_sample(sto, name):
         assert np.array_equal(u[b], t[3:-3]) and np.array_equal(cx[b], ocx) and np.array_equal(cy[b], ocy)
         assert np.array_equal(t, d["ref_t"][b])                       # knots: exact vs FITPACK
         assert rel_err(cx[b], d["ref_cx"][b]) < 1e-9 and rel_err(cy[b], d["ref_cy"][b]) < 1e-9
+        if solver == "fitpack":                                       # the reference's own coefficients and samples
+            assert np.array_equal(cx[b], d["ref_cx"][b]) and np.array_equal(cy[b], d["ref_cy"][b])
+            assert np.array_equal(X[b], d["ref_X"][b]) and np.array_equal(Y[b], d["ref_Y"][b])
+            assert rel_err(R[b], d["ref_CURVATURE"][b]) < 1e-15
         oX, oY, oYAW, oR = O.sample(t, ocx, ocy, 3, d["ts"], 0)
         assert np.array_equal(X[b], oX) and np.array_equal(Y[b], oY) and np.array_equal(R[b], oR)
         assert np.max(np.abs(YAW[b] - oYAW)) < 1e-14                  # device atan2 vs libm
@@ -142,7 +148,7 @@ def test_qss_synthetic_tables(sto, impl):
 
 @pytest.mark.parametrize("name", CAND_CASES)
 @pytest.mark.parametrize("impl", ["plain", "memo"])
-@pytest.mark.parametrize("solver", ["thomas", "partitioned"])
+@pytest.mark.parametrize("solver", ["fitpack", "thomas", "partitioned"])
 def test_fused_lap_time(sto, name, impl, solver):
     d = golden(name)
     ev = _evaluator(sto, d, impl=impl)
@@ -164,6 +170,8 @@ def test_fused_lap_time(sto, name, impl, solver):
         for b in range(B):
             assert lap[b] == oracle_lap_from_coefficients(O, u[b], cx[b], cy[b], d["ts"], None, ov)
         assert np.max(np.abs(lap - d["ref_lap"])) < 1e-6                  # BASELINE: lap within 1e-6 s of the reference
+        if solver == "fitpack":                                          # reference coefficients: only x*x vs pow(x, 2) is left
+            assert np.max(np.abs(lap - d["ref_lap"])) < 1e-10
         # host-buffer entry point (H2D + transpose + D2H inside) returns the same bits
         hlap, hst = ev.lap_times_host(d["offsets"])
         assert np.array_equal(hlap, lap) and not hst.any()
@@ -236,7 +244,7 @@ def test_edge_cases(sto):
     # M = 3: the smallest closed line FITPACK accepts (trajectory.py:214)
     tri = np.array([[[0.0, 0.0], [40.0, 0.0], [20.0, 30.0]]])
     z = np.zeros((1, 5))
-    for solver in ("thomas", "partitioned"):
+    for solver in ("fitpack", "thomas", "partitioned"):
         with fit_solver(solver):
             t, ocx, ocy = O.fit_periodic_cubic(tri[0])
             u, cx, cy, st = ev.fit(points_sm=(to_sm(tri[:, :, 0]), to_sm(tri[:, :, 1])), B=1)
@@ -346,20 +354,23 @@ def test_long_track_quarter_metre(sto):
     ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
     from spline_trajectory_optimization_b200 import _lib
     lib = _lib.load()
-    lap, st = ev.lap_times(to_sm(off), B=B)       # automatic plan: 32 lanes share each candidate's cyclic solve
-    assert lib.sto_fit_partition_lanes(M, B) == 32
+    lap, st = ev.lap_times(to_sm(off), B=B)       # default solver: FITPACK's Givens sweep, a 116 k-rotation chain per line
     lap = lap.cpu().numpy()
     assert not st.cpu().numpy().any()
     g = golden("cand_m579_n579")
+    ov = O.make_vehicle(*veh_args(g))
     olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
-                            np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=4, ref_pow=0)
+                            np.zeros(M), ov, n_threads=4, ref_pow=0)
     assert not ost.any() and np.array_equal(lap, olap)
-    with fit_solver("thomas"):               # the one-lane Thomas chain of 23 k rows
-        lap_t, st_t = ev.lap_times(to_sm(off[:2]), B=2)
-        olap_t, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:2], rt.center_d.ts(),
-                                np.zeros(M), O.make_vehicle(*veh_args(g)), n_threads=2, ref_pow=0)
-    assert not st_t.cpu().numpy().any() and np.array_equal(lap_t.cpu().numpy(), olap_t)
-    assert np.max(np.abs(olap_t - olap[:2])) < 1e-6
+    for solver in ("partitioned", "thomas"):   # 32 lanes share each line's cyclic solve / the one-lane chain of 23 k rows
+        with fit_solver(solver):
+            if solver == "partitioned":
+                assert lib.sto_fit_solver_lanes(M, 2) == 32
+            lap_s, st_s = ev.lap_times(to_sm(off[:2]), B=2)
+            olap_s, _ = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:2], rt.center_d.ts(),
+                                    np.zeros(M), ov, n_threads=2, ref_pow=0)
+        assert not st_s.cpu().numpy().any() and np.array_equal(lap_s.cpu().numpy(), olap_s)
+        assert np.max(np.abs(olap_s - olap[:2])) < 1e-4       # schedule bifurcations allowed
 
 
 def test_fit_partitioned_on_device(sto):
@@ -375,28 +386,25 @@ def test_fit_partitioned_on_device(sto):
         d = golden(name)
         ev = _evaluator(sto, d)
         B, M = d["offsets"].shape
-        assert lib.sto_fit_partition_lanes(M, B) == 32 and lib.sto_fit_partition_lanes(M, 4096) == 8
-        assert lib.sto_fit_partition_lanes(M, 1 << 20) == 1 and lib.sto_fit_partition_lanes(100, 4) == 1
         hu, hcx, hcy, _ = H.fit_points(d["points"], -1)
-        try:
-            for lanes in (32, 16, 8, 4, 2, 1):
-                os.environ["STO_FIT_SPLIT"] = str(lanes)
-                u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
-                torch.cuda.synchronize()
-                assert not st[:B].any()
-                u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
-                assert np.array_equal(u, hu) and np.array_equal(cx, hcx) and np.array_equal(cy, hcy), lanes
-        finally:
-            del os.environ["STO_FIT_SPLIT"]
-        lap1, st1 = ev.lap_times(to_sm(d["offsets"]), B=B)
-        lib.sto_set_fit_partition(0)
-        try:
-            assert lib.sto_fit_partition_lanes(M, B) == 0
+        with fit_solver("partitioned"):
+            assert lib.sto_fit_solver_lanes(M, B) == 32 and lib.sto_fit_solver_lanes(M, 4096) == 8
+            assert lib.sto_fit_solver_lanes(M, 1 << 20) == 1 and lib.sto_fit_solver_lanes(100, 4) == 1
+            try:
+                for lanes in (32, 16, 8, 4, 2, 1):
+                    os.environ["STO_FIT_SPLIT"] = str(lanes)
+                    u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
+                    torch.cuda.synchronize()
+                    assert not st[:B].any()
+                    u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+                    assert np.array_equal(u, hu) and np.array_equal(cx, hcx) and np.array_equal(cy, hcy), lanes
+            finally:
+                del os.environ["STO_FIT_SPLIT"]
+            lap1, st1 = ev.lap_times(to_sm(d["offsets"]), B=B)
+        with fit_solver("thomas"):
             u0, cx0, cy0, _ = ev.fit(to_sm(d["offsets"]), B=B)
             lap0, _ = ev.lap_times(to_sm(d["offsets"]), B=B)
             torch.cuda.synchronize()
-        finally:
-            lib.sto_set_fit_partition(-1)
         assert np.array_equal(u, to_cm(u0, B))
         assert rel_err(cx, to_cm(cx0, B)) < 1e-12 and rel_err(cy, to_cm(cy0, B)) < 1e-12
         assert rel_err(cx, d["ref_cx"]) < 1e-9 and rel_err(cy, d["ref_cy"]) < 1e-9
@@ -422,20 +430,25 @@ def test_fit_partitioned_quarter_metre(sto):
     M = len(rt.center_d)
     nrm = rt.left_normals()
     ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()))
-    assert lib.sto_fit_partition_lanes(M, 4) == 32 and lib.sto_fit_partition_lanes(M, 20000) == 4 and lib.sto_fit_partition_lanes(M, 40000) == 2
     off = candidates.smooth_offsets(M, 600, rt.dist_to_left, rt.dist_to_right, seed=3)
     hu, hcx, hcy, _ = H.fit_offsets(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[:3], split=-1)
-    for B in (1, 3, 70, 600):       # 32, 32, 32 and 16 lanes per line
-        u, cx, cy, st = ev.fit(to_sm(off[:B]), B=B)
-        torch.cuda.synchronize()
-        assert not st[:B].any()
-        u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
-        nb = min(B, 3)
-        assert np.array_equal(u[:nb], hu[:nb]) and np.array_equal(cx[:nb], hcx[:nb]) and np.array_equal(cy[:nb], hcy[:nb])
+    with fit_solver("partitioned"):
+        assert lib.sto_fit_solver_lanes(M, 4) == 32 and lib.sto_fit_solver_lanes(M, 20000) == 4
+        assert lib.sto_fit_solver_lanes(M, 40000) == 2
+        for B in (1, 3, 70, 600):       # 32, 32, 32 and 16 lanes per line
+            u, cx, cy, st = ev.fit(to_sm(off[:B]), B=B)
+            torch.cuda.synchronize()
+            assert not st[:B].any()
+            u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
+            nb = min(B, 3)
+            assert np.array_equal(u[:nb], hu[:nb]) and np.array_equal(cx[:nb], hcx[:nb]) and np.array_equal(cy[:nb], hcy[:nb])
     pts = rt.center_d[None, :, :2] + off[:3, :, None] * nrm[None]
+    fu, fcx, fcy, fst = ev.fit(to_sm(off[:3]), B=3)            # default: FITPACK's sweep, 23 k rows
+    fcx, fcy = to_cm(fcx, 3), to_cm(fcy, 3)
     for b in range(3):
-        t, ocx, ocy = O.fit_periodic_cubic(pts[b])
+        t, ocx, ocy = O.fit_periodic_cubic(pts[b])             # oracle default = FITPACK restatement
         assert np.array_equal(hu[b], t[3:-3])
+        assert np.array_equal(fcx[b], ocx) and np.array_equal(fcy[b], ocy)
         assert rel_err(hcx[b], ocx) < 1e-12 and rel_err(hcy[b], ocy) < 1e-12
 
 
@@ -556,3 +569,17 @@ def test_fill_bounds_on_device(sto):
     far[0, Trajectory.X], far[0, Trajectory.Y] = 1e5, 1e5
     far.fill_bounds(rt.left_r, rt.right_r, max_dist=100.0)
     assert far[0, Trajectory.LEFT_BOUND_X] == 1e5 and far[0, Trajectory.RIGHT_BOUND_Y] == 1e5
+
+
+def test_fast_fp64_division_and_sqrt_selftest(sto):
+    """The FITPACK solver's rotation chain runs its divisions and square roots as flagged, branch-free copies of nvcc's
+    fast paths (csrc/sto_common.cuh).  On 3 x 2^27 operations over every kind of operand: not one result differs from the
+    plain operators while the flag is down; the flag is up only for operands outside the fast path's range."""
+    import ctypes
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    for seed in (1, 2, 3):
+        tested, bad, flagged = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(lib.sto_selftest_fp64(seed, ctypes.byref(tested), ctypes.byref(bad), ctypes.byref(flagged)))
+        assert tested.value == 1 << 27 and bad.value == 0
+        assert 0 < flagged.value < tested.value // 2      # random bit patterns hit the guards; in-range operands do not

@@ -12,17 +12,21 @@ from helpers import CAND_CASES, SIM_CASES, golden, rel_err, veh_args
 @pytest.fixture(autouse=True)
 def _default_oracle_solver():
     yield
-    O.set_fit_solver("blocks")
+    O.set_fit_solver("fitpack")
 
 
 @pytest.mark.parametrize("name", CAND_CASES[:2])
-@pytest.mark.parametrize("solver", ["thomas", "blocks"])
+@pytest.mark.parametrize("solver", ["fitpack", "thomas", "blocks"])
 def test_fit_and_eval_bit_exact(name, solver):
-    """Host build of the device fit (both solvers) == the oracle's restatement of the same solver, bit for bit."""
+    """Host build of the device fit (all three solvers) == the oracle's restatement of the same solver, bit for bit;
+    the FITPACK solver == the reference's own coefficients (golden, from the unmodified reference) bit for bit."""
     d = golden(name)
     O.set_fit_solver(solver)
-    u, cx, cy, st = H.fit_points(d["points"], 1 if solver == "thomas" else -1)
+    u, cx, cy, st = H.fit_points(d["points"], {"thomas": 1, "blocks": -1, "fitpack": -108}[solver])
     assert not st.any()
+    if solver == "fitpack":
+        assert np.array_equal(cx, d["ref_cx"]) and np.array_equal(cy, d["ref_cy"])
+        assert np.array_equal(H.fit_points(d["points"], -101)[1], cx)        # any split of the row phases
     E = H.evaluate(u, cx, cy, d["ts"])
     for b in range(d["points"].shape[0]):
         t, ocx, ocy = O.fit_periodic_cubic(d["points"][b])
@@ -162,6 +166,7 @@ def test_fit_partitioned_solver(name):
     d = golden(name)
     u0, cx0, cy0, _ = H.fit_points(d["points"], 1)
     ref = None
+    assert rel_err(cx0, d["ref_cx"]) < 1e-9
     for lanes in (1, 4, 32):
         u, cx, cy, st = H.fit_points(d["points"], -lanes)
         assert not st.any() and np.array_equal(u, u0)
@@ -228,3 +233,24 @@ def test_fit_lsq_flags_empty_knot_interval():
     t = np.concatenate([inner[-k - 1:-1] - per, inner, inner[1:k + 1] + per])
     u, cx, cy, st = H.fit_lsq(pts, t, k)
     assert not st.any() and np.isfinite(cx).all()
+
+
+def test_fit_fitpack_small_and_random_lines():
+    """FITPACK restatement vs SciPy itself (run here as the checker): bit for bit from the smallest closed line
+    (M = 3, where the periodic wrap folds back onto the border block) upwards."""
+    import warnings
+    from scipy.interpolate import splprep
+    rng = np.random.default_rng(3)
+    for M in (3, 4, 5, 6, 7, 10, 33, 100, 300):
+        for rep in range(6):
+            th = np.sort(rng.uniform(0, 2 * np.pi, M))
+            pts = np.stack([np.cos(th) * (1 + 0.2 * rng.standard_normal(M)), 0.7 * np.sin(th) + 0.1 * rng.standard_normal(M)], -1)
+            c = np.vstack([pts, pts[:1]])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                (t, (rx, ry), k), u = splprep([c[:, 0], c[:, 1]], s=0.0, k=3, per=1)
+            hu, hcx, hcy, st = H.fit_points(pts[None], -101)
+            assert not st.any() and np.array_equal(hu[0], u)
+            assert np.array_equal(hcx[0], rx) and np.array_equal(hcy[0], ry), (M, rep)
+            ot, ocx, ocy = O.fit_periodic_cubic(pts)
+            assert np.array_equal(ot, t) and np.array_equal(ocx, rx) and np.array_equal(ocy, ry), (M, rep)

@@ -26,9 +26,9 @@ if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_benc
     for B in [int(x) for x in os.environ.get("SWEEP_B", "256,1024,4096,16384").split(",")]:
         off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
         line = f"M={M} B={B:6d}"
-        for mode, lanes in ((0, 1), (0, 2), (0, 8), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
+        for mode, lanes in ((2, 1), (2, 4), (2, 8), (2, 16), (2, 32), (0, 1), (0, 2), (0, 8), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
             os.environ["STO_FIT_SPLIT"] = str(lanes)
-            lib.sto_set_fit_partition(mode)
+            lib.sto_set_fit_solver(mode)
             best = 1e9
             for it in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,17 +37,17 @@ if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_benc
                 e1.record()
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
-            line += f"  {'part' if mode else 'thomas'}x{lanes}: {best:8.2f} ms"
+            line += f"  {('thomas', 'blocks', 'fitpack')[mode]}x{lanes}: {best:8.2f} ms"
         print(line, flush=True)
     del os.environ["STO_FIT_SPLIT"]
-    lib.sto_set_fit_partition(-1)
+    lib.sto_set_fit_solver(2)
     sys.exit(0)
 for B in (1, 64, 1024, 4096, 16384):
     off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
     res = {}
-    for mode, name in ((0, "one-lane"), (1, "partitioned")):
-        lib.sto_set_fit_partition(mode)
-        lanes = lib.sto_fit_partition_lanes(M, B)
+    for mode, name in ((0, "one-lane"), (1, "partitioned"), (2, "fitpack")):
+        lib.sto_set_fit_solver(mode)
+        lanes = lib.sto_fit_solver_lanes(M, B)
         best = 1e9
         for it in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,8 +57,8 @@ for B in (1, 64, 1024, 4096, 16384):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         res[name] = (best, lanes, cx[:, :B].clone())
-    lib.sto_set_fit_partition(-1)
-    a, b = res["one-lane"], res["partitioned"]
-    err = float(((a[2] - b[2]).abs().max() / a[2].abs().max()).item())
-    print(f"M={M} B={B:6d}  one-lane {a[0]:9.3f} ms   partitioned ({b[1]:2d} lanes) {b[0]:9.3f} ms   speed-up {a[0] / b[0]:6.2f}x   "
-          f"auto plan lanes {lib.sto_fit_partition_lanes(M, B)}   max |dc|/|c| {err:.2e}", flush=True)
+    lib.sto_set_fit_solver(2)
+    a, b, f = res["one-lane"], res["partitioned"], res["fitpack"]
+    err = float(((f[2] - b[2]).abs().max() / f[2].abs().max()).item())
+    print(f"M={M} B={B:6d}  fitpack {f[0]:9.3f} ms   thomas {a[0]:9.3f} ms   blocks ({b[1]:2d} lanes) {b[0]:9.3f} ms   "
+          f"max |dc|/|c| blocks vs fitpack {err:.2e}", flush=True)
