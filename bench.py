@@ -270,6 +270,17 @@ def run_gpu_arm(args):
         buf = (ctypes.c_float * 4)()
         _lib.check(lib.sto_last_stage_ms(buf))
         stage[j] = list(buf)
+    # informational: the same step with the lane-group block / cyclic-reduction fit solver (coefficients equal to
+    # FITPACK's up to rounding instead of bit for bit)
+    _lib.check(lib.sto_set_fit_solver(_lib.FIT_BLOCKS))
+    stage_b = np.zeros((min(args.steps, 4), 4), dtype=np.float32)
+    for j in range(stage_b.shape[0]):
+        ev.lap_times(d_off[j & 1], B=B, out=lap, status=st)
+        buf = (ctypes.c_float * 4)()
+        _lib.check(lib.sto_last_stage_ms(buf))
+        stage_b[j] = list(buf)
+    _lib.check(lib.sto_set_fit_solver(_lib.FIT_FITPACK))
+    ev.lap_times(d_off[(args.steps - 1) & 1], B=B, out=lap, status=st)   # `lap` again holds the default solver's result
     lib.sto_set_stage_timing(0)
     fp64_peak = ctypes.c_double(0.0)
     _lib.check(lib.sto_measure_fp64_peak(ctypes.byref(fp64_peak)))
@@ -311,6 +322,8 @@ def run_gpu_arm(args):
             "config": {"workload": "BASELINE configs[1]: Monza, 4,096 lateral-offset candidates/GPU at 2 m "
                                    "(M=N=2895), FP64, exact reference QSS schedule",
                        "candidates_per_gpu": B, "M": M, "N": N, "qss_impl": args.qss,
+                       "fit_solver": "fitpack: FITPACK's fpclos Givens sweep restated bit for bit (coefficients identical "
+                                     "to the reference's scipy splprep)",
                        "l2": "two alternating candidate batches; one step touches ~1.5 GB (> 126 MB L2)",
                        "parallelism": f"candidate-sharded x{world}; all-gather of (lap, index) + argmin"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * M * B),
@@ -342,6 +355,12 @@ def run_gpu_arm(args):
                      "frac_executed": (60 * M + 200 * N + 70 * 24618) * B / (float(stage_ms.sum()) * 1e-3) / 1e12 / max(fp64_peak.value, 1e-9),
                      "note": "front-step / evaluation counts of the centre line (tests/hostsim counters); the path is "
                              "bound by the per-line dependent chain of FP64 divisions and square roots, see DESIGN.md"},
+            "fast_fit_solver": {"solver": "blocks (lane groups: 32-block elimination + PCR over warp shuffles)",
+                                "stage_ms": {"fit": float(stage_b.mean(axis=0)[1]), "sample": float(stage_b.mean(axis=0)[2]),
+                                             "qss": float(stage_b.mean(axis=0)[3])},
+                                "value": B * world / (float(stage_b.mean(axis=0).sum()) * 1e-3), "unit": UNIT,
+                                "note": "coefficients within 2e-15 of FITPACK's; 1-2 lines in 500 then differ from the "
+                                        "reference's lap by 1e-6..1e-4 s (schedule bifurcations), hence not the default"},
             "clocks": clocks,
             "lap_min_s": float(np.min(lap_host)), "lap_centre_line_s": float(lap_host[0]), "all_status_ok": ok,
         }
