@@ -759,7 +759,8 @@ STO_HD void fp_wrap_step(FpWrapRow& r, int jj, int n10, double& a1, double& a2, 
     if (i2 >= 2) r.hc = 0.0; else r.hb = 0.0;   // h1(i2 + 1) = 0
 }
 
-STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
+// Part 1 (one lane): rows 1 .. M-2 into the band, the a2 block, the two periodic rows ready to travel.
+STO_HD void fitpack_regular(const FitArgs& A, int b, FpWrapRow* wr, double* init21, double* init22) {
     const int M = A.M, ld = A.ld;
     const int n7 = M, kk = 2, n10 = n7 - kk;   // kk1 = 3
     double* const a11 = A.cp; double* const a12 = A.zx; double* const a13 = A.zy;   // a1(j, 1..3), rows 0-based
@@ -837,7 +838,7 @@ STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
     z1[at(M - 1, ld, b)] = q2[0]; z2[at(M - 1, ld, b)] = q2[1];
     // ---- a2: the last two columns of the band, as a dense M x 2 block (zero except six entries; the zeros of rows
     //      1 .. n10 are supplied on the fly below, where those rows are first touched) ---------------------------------
-    double init21[3] = {0.0, 0.0, 0.0}, init22[3] = {0.0, 0.0, 0.0};   // a2(n10 - 1 + k, 1..2), k = 0..2 (rows M-3 .. M-1, 0-based)
+    for (int k = 0; k < 3; ++k) { init21[k] = 0.0; init22[k] = 0.0; }   // a2(n10 - 1 + k, 1..2), k = 0..2 (rows M-3 .. M-1, 0-based)
     {
         int jk = n10 + 1;                      // 1-based as in fpclos
         for (int i = 1; i <= kk; ++i) {
@@ -860,7 +861,6 @@ STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
     // ---- rows M-1 and M: the periodicity condition couples them to the first columns.  Both rows travel through the
     //      band together: row M-1 rotates against band row jj, then row M against the updated band row (exactly the
     //      order of two successive sweeps, since neither revisits a band row) ----------------------------------------
-    FpWrapRow wr[2];
     for (int r = 0; r < 2; ++r) {
         const int it = M - 1 + r;              // 1-based row number
         const int l5 = it - 1;
@@ -880,6 +880,16 @@ STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
         }
         wr[r].ha = h1[1]; wr[r].hb = h1[2]; wr[r].hc = h1[3]; wr[r].g1 = h2[1]; wr[r].g2 = h2[2];
     }
+}
+
+// Part 2, one-lane form: both periodic rows through band rows 1 .. n10 (host build; device when a line has one lane).
+STO_HD void fitpack_sweep(const FitArgs& A, int b, FpWrapRow* wr, const double* init21, const double* init22) {
+    const int M = A.M, ld = A.ld;
+    const int n7 = M, kk = 2, n10 = n7 - kk;   // kk1 = 3
+    double* const a11 = A.cp; double* const a12 = A.zx; double* const a13 = A.zy;   // a1(j, 1..3), rows 0-based
+    double* const a21 = A.zz; double* const a22 = A.ze;                            // a2(j, 1..2)
+    double* const z1 = A.cx; double* const z2 = A.cy;                              // right-hand sides, then c in place
+    (void)n7; (void)a11; (void)a12; (void)a13; (void)a21; (void)a22; (void)z1; (void)z2; (void)n10;
     double na1[STO_FP_CHUNK], na2[STO_FP_CHUNK], na3[STO_FP_CHUNK], nzx[STO_FP_CHUNK], nzy[STO_FP_CHUNK];
 #pragma unroll
     for (int c = 0; c < STO_FP_CHUNK; ++c) {
@@ -915,6 +925,16 @@ STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
             a21[at(jj - 1, ld, b)] = b1; a22[at(jj - 1, ld, b)] = b2;
         }
     }
+}
+
+// Part 3 (one lane): the border rows of a2, then fpbacp.
+STO_HD void fitpack_finish(const FitArgs& A, int b, FpWrapRow* wr) {
+    const int M = A.M, ld = A.ld;
+    const int n7 = M, kk = 2, n10 = n7 - kk;   // kk1 = 3
+    double* const a11 = A.cp; double* const a12 = A.zx; double* const a13 = A.zy;   // a1(j, 1..3), rows 0-based
+    double* const a21 = A.zz; double* const a22 = A.ze;                            // a2(j, 1..2)
+    double* const z1 = A.cx; double* const z2 = A.cy;                              // right-hand sides, then c in place
+    (void)n7; (void)a11; (void)a12; (void)a13; (void)a21; (void)a22; (void)z1; (void)z2; (void)n10;
     for (int r = 0; r < 2; ++r) {              // rotation with rows n10+1 .. n7 of a2 (row M-1 completely, then row M)
         double gg[3] = {0.0, wr[r].g1, wr[r].g2};
         for (int jj = 1; jj <= kk; ++jj) {
@@ -1008,6 +1028,110 @@ STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
     }
 }
 
+#if defined(__CUDA_ARCH__)
+// Part 2, two-lane form: lane g = 0 carries row M-1, lane g = 1 row M one band row behind; the band row travels from
+// lane 0 to lane 1 by __shfl_sync after lane 0's rotation and is stored by lane 1.  Each lane performs exactly the
+// rotations fitpack_sweep performs for its row, on the same operands, so the result is bit-identical; the chain is
+// n10 + 1 rotations long instead of 2 n10.  Whole warps call this (lanes g >= 2 only take part in the shuffles).
+STO_D void fitpack_sweep_pair(const FitArgs& A, int b, bool active, int g, int lane0, FpWrapRow& mine,
+                              const double* init21, const double* init22) {
+    const int M = A.M, ld = A.ld, n10 = M - 2;
+    double* const a11 = A.cp; double* const a12 = A.zx; double* const a13 = A.zy;
+    double* const a21 = A.zz; double* const a22 = A.ze;
+    double* const z1 = A.cx; double* const z2 = A.cy;
+    const bool lead = active && g == 0, follow = active && g == 1;
+    double na1[STO_FP_CHUNK], na2[STO_FP_CHUNK], na3[STO_FP_CHUNK], nzx[STO_FP_CHUNK], nzy[STO_FP_CHUNK];
+#pragma unroll
+    for (int c = 0; c < STO_FP_CHUNK; ++c) {
+        const int jj = 1 + c;
+        na1[c] = na2[c] = na3[c] = nzx[c] = nzy[c] = 0.0;
+        if (lead && jj <= n10) {
+            na1[c] = a11[at(jj - 1, ld, b)]; na2[c] = a12[at(jj - 1, ld, b)]; na3[c] = a13[at(jj - 1, ld, b)];
+            nzx[c] = z1[at(jj - 1, ld, b)]; nzy[c] = z2[at(jj - 1, ld, b)];
+        }
+    }
+    double p1 = 0.0, p2 = 0.0, p3 = 0.0, pb1 = 0.0, pb2 = 0.0, pzx = 0.0, pzy = 0.0;   // band row handed to lane 1
+    for (int j0 = 1; j0 <= n10 + 1; j0 += STO_FP_CHUNK) {
+        double ra1[STO_FP_CHUNK], ra2[STO_FP_CHUNK], ra3[STO_FP_CHUNK], rzx[STO_FP_CHUNK], rzy[STO_FP_CHUNK];
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) { ra1[c] = na1[c]; ra2[c] = na2[c]; ra3[c] = na3[c]; rzx[c] = nzx[c]; rzy[c] = nzy[c]; }
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int jj = j0 + STO_FP_CHUNK + c;
+            if (lead && jj <= n10) {
+                na1[c] = a11[at(jj - 1, ld, b)]; na2[c] = a12[at(jj - 1, ld, b)]; na3[c] = a13[at(jj - 1, ld, b)];
+                nzx[c] = z1[at(jj - 1, ld, b)]; nzy[c] = z2[at(jj - 1, ld, b)];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < STO_FP_CHUNK; ++c) {
+            const int step = j0 + c;
+            if (step > n10 + 1) break;               // warp-uniform
+            const int jj = step - g;                 // lane 0: band row `step`; lane 1: the row lane 0 did one step ago
+            double r1, r2, r3, b1, b2, zx, zy;
+            if (g == 0) {
+                const int slot = jj - (n10 - 1);     // the two band rows that already carry a2 entries
+                r1 = ra1[c]; r2 = ra2[c]; r3 = ra3[c]; zx = rzx[c]; zy = rzy[c];
+                b1 = (slot >= 0 && slot < 3) ? init21[slot] : 0.0;
+                b2 = (slot >= 0 && slot < 3) ? init22[slot] : 0.0;
+            } else {
+                r1 = p1; r2 = p2; r3 = p3; b1 = pb1; b2 = pb2; zx = pzx; zy = pzy;
+            }
+            const bool on = (lead || follow) && jj >= 1 && jj <= n10;
+            if (on) fp_wrap_step(mine, jj, n10, r1, r2, r3, b1, b2, zx, zy);
+            if (on && g == 1) {
+                a11[at(jj - 1, ld, b)] = r1; a12[at(jj - 1, ld, b)] = r2; a13[at(jj - 1, ld, b)] = r3;
+                z1[at(jj - 1, ld, b)] = zx; z2[at(jj - 1, ld, b)] = zy;
+                a21[at(jj - 1, ld, b)] = b1; a22[at(jj - 1, ld, b)] = b2;
+            }
+            p1 = __shfl_sync(0xffffffffu, r1, lane0); p2 = __shfl_sync(0xffffffffu, r2, lane0);
+            p3 = __shfl_sync(0xffffffffu, r3, lane0); pb1 = __shfl_sync(0xffffffffu, b1, lane0);
+            pb2 = __shfl_sync(0xffffffffu, b2, lane0); pzx = __shfl_sync(0xffffffffu, zx, lane0);
+            pzy = __shfl_sync(0xffffffffu, zy, lane0);
+        }
+    }
+}
+
+STO_D FpWrapRow fp_shfl_row(const FpWrapRow& r, int src) {
+    FpWrapRow o;
+    o.ha = __shfl_sync(0xffffffffu, r.ha, src); o.hb = __shfl_sync(0xffffffffu, r.hb, src);
+    o.hc = __shfl_sync(0xffffffffu, r.hc, src); o.g1 = __shfl_sync(0xffffffffu, r.g1, src);
+    o.g2 = __shfl_sync(0xffffffffu, r.g2, src); o.x = __shfl_sync(0xffffffffu, r.x, src);
+    o.y = __shfl_sync(0xffffffffu, r.y, src);
+    return o;
+}
+
+// The FITPACK solver for lane g of a group of G lanes (whole warps call this): one lane per line, except that the two
+// periodic rows travel through the band on two lanes when the group has them.
+STO_D void fit_solve_fitpack_lane(const FitArgs& A, int b, bool active, int g, int G, int lane0) {
+    FpWrapRow wr[2];
+    wr[0] = FpWrapRow{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    wr[1] = wr[0];
+    double init21[3] = {0.0, 0.0, 0.0}, init22[3] = {0.0, 0.0, 0.0};
+    if (active && g == 0) fitpack_regular(A, b, wr, init21, init22);
+    if (G >= 2) {
+        const FpWrapRow second = fp_shfl_row(wr[1], lane0);          // row M goes to lane 1
+        FpWrapRow mine = (g == 0) ? wr[0] : second;
+        fitpack_sweep_pair(A, b, active, g, lane0, mine, init21, init22);
+        const FpWrapRow back = fp_shfl_row(mine, lane0 + 1);         // ... and comes back for the border rows
+        if (g == 0) { wr[0] = mine; wr[1] = back; }
+        __syncwarp();                                                // lane 1's band rows are visible to lane 0
+    } else if (active) {
+        fitpack_sweep(A, b, wr, init21, init22);
+    }
+    if (active && g == 0) fitpack_finish(A, b, wr);
+}
+#endif
+
+// The FITPACK solver played by one caller (host build: the reference for what the lanes do).
+STO_HD void fit_solve_fitpack(const FitArgs& A, int b) {
+    FpWrapRow wr[2];
+    double init21[3], init22[3];
+    fitpack_regular(A, b, wr, init21, init22);
+    fitpack_sweep(A, b, wr, init21, init22);
+    fitpack_finish(A, b, wr);
+}
+
 STO_HD void fit_degenerate(const FitArgs& A, int b) {  // FITPACK returns ier=10; scipy raises
     const int M = A.M, ld = A.ld;
     if (A.status) A.status[b] |= STO_CAND_DEGENERATE_FIT;
@@ -1039,7 +1163,11 @@ STO_HD void fit_candidate_lane(const FitArgs& A, int b, bool active, int g, int 
     if (PART_E < 0) {
         if (active && ok) fit_phase_bspl_rows(A, b, g, G);
         STO_FIT_SYNC();
+#if defined(__CUDA_ARCH__)
+        fit_solve_fitpack_lane(A, b, active && ok, g, G, lane0);
+#else
         if (active && ok && g == 0) fit_solve_fitpack(A, b);
+#endif
         return;
     }
     if (active && ok) fit_phase_rows(A, b, g, G);
