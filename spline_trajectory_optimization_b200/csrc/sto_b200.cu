@@ -76,7 +76,18 @@ FitPlan pick_fit_plan(int M, int B) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) solver = v;
     }
-    if (solver != STO_FIT_BLOCKS) return FitPlan{pick_fit_split(B), solver};
+    if (solver == STO_FIT_THOMAS) return FitPlan{pick_fit_split(B), solver};
+    if (solver == STO_FIT_FITPACK) {
+        // the rotation chain runs on one lane (two for the periodic rows); the other lanes of a group only speed up the
+        // row phases (segments, running sum, fpbspl values).  Measured (M = 2895): B = 64: 5.1 / 5.4 / 5.7 ms at
+        // 32 / 16 / 8 lanes; B = 4,096: 7.1 ms at 8 lanes, 12.7 at 16
+        int lanes = (B <= 256) ? 32 : (B <= 1024) ? 16 : pick_fit_split(B);
+        if (const char* e = getenv("STO_FIT_SPLIT")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
+        }
+        return FitPlan{lanes, solver};
+    }
     int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 24576) ? 4 : (B <= 49152) ? 2 : 1;
     if (const char* e = getenv("STO_FIT_SPLIT")) {
         const int v = atoi(e);

@@ -733,6 +733,12 @@ STO_HD void fit_phase_bspl_rows(const FitArgs& A, int b, int g, int G) {
         A.cp[at(i, ld, b)] = h[0];
         A.zx[at(i, ld, b)] = h[1];
         A.zy[at(i, ld, b)] = h[2];
+        // ... and the point itself goes where row i of the right-hand side z will be stored (one strided load per
+        // row in the rotation chain instead of an offset, four track values and the arithmetic)
+        double px, py;
+        fit_point(A, i, b, px, py);
+        A.cx[at(i, ld, b)] = px;
+        A.cy[at(i, ld, b)] = py;
     }
 }
 
@@ -767,10 +773,11 @@ STO_HD void fitpack_regular(const FitArgs& A, int b, FpWrapRow* wr, double* init
     double* const a21 = A.zz; double* const a22 = A.ze;                            // a2(j, 1..2)
     double* const z1 = A.cx; double* const z2 = A.cy;                              // right-hand sides, then c in place
     // B-spline values of the two periodic rows (their slots are overwritten at the end of the regular sweep)
-    double hp[2][3];
+    double hp[2][3], pp[2][2];
     for (int r = 0; r < 2; ++r) {
         const int i = M - 2 + r;
         hp[r][0] = a11[at(i, ld, b)]; hp[r][1] = a12[at(i, ld, b)]; hp[r][2] = a13[at(i, ld, b)];
+        pp[r][0] = z1[at(i, ld, b)]; pp[r][1] = z2[at(i, ld, b)];
     }
     // ---- rows 1 .. M-2: rotate into a1 (three rows of a1 and z live in registers; row `it` is final afterwards) ------
     double w1[3] = {0.0, 0.0, 0.0}, w2[3] = {0.0, 0.0, 0.0}, w3[3] = {0.0, 0.0, 0.0};
@@ -783,7 +790,7 @@ STO_HD void fitpack_regular(const FitArgs& A, int b, FpWrapRow* wr, double* init
         nhs[c][0] = nhs[c][1] = nhs[c][2] = nps[c][0] = nps[c][1] = 0.0;
         if (c < M - 2) {
             nhs[c][0] = a11[at(c, ld, b)]; nhs[c][1] = a12[at(c, ld, b)]; nhs[c][2] = a13[at(c, ld, b)];
-            fit_point(A, c, b, nps[c][0], nps[c][1]);
+            nps[c][0] = z1[at(c, ld, b)]; nps[c][1] = z2[at(c, ld, b)];
         }
     }
     for (int i0 = 0; i0 < M - 2; i0 += STO_FP_CHUNK) {
@@ -797,7 +804,7 @@ STO_HD void fitpack_regular(const FitArgs& A, int b, FpWrapRow* wr, double* init
             const int i = i0 + STO_FP_CHUNK + c;
             if (i < M - 2) {
                 nhs[c][0] = a11[at(i, ld, b)]; nhs[c][1] = a12[at(i, ld, b)]; nhs[c][2] = a13[at(i, ld, b)];
-                fit_point(A, i, b, nps[c][0], nps[c][1]);
+                nps[c][0] = z1[at(i, ld, b)]; nps[c][1] = z2[at(i, ld, b)];
             }
         }
 #pragma unroll
@@ -866,7 +873,7 @@ STO_HD void fitpack_regular(const FitArgs& A, int b, FpWrapRow* wr, double* init
         const int l5 = it - 1;
         const double h[4] = {0.0, hp[r][0], hp[r][1], hp[r][2]};
         double h1[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, h2[4] = {0.0, 0.0, 0.0, 0.0};
-        fit_point(A, it - 1, b, wr[r].x, wr[r].y);
+        wr[r].x = pp[r][0]; wr[r].y = pp[r][1];
         int j = l5 - n10;
         for (int i = 1; i <= 3; ++i) {
             ++j;
