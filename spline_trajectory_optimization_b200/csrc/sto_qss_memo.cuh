@@ -802,6 +802,135 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
     return w;
 }
 
+// ---- lane groups: the list WALK itself spread over the lanes --------------------------------------------------------
+// The one-at-a-time walkers above make every lane of a group read, classify and re-store every list entry redundantly:
+// a chain of ring read -> sample index -> plane test -> store per entry, ~430 cycles each, and 42 k visits per Monza line
+// on the forward list (half of that sub-pass's time, 19 % of the kernel; tools/phase_profile.py).  Here lane g owns the
+// entries g, g + G, g + 2G, ... of the list (its prefetch ring holds the next STO_LIST_RING of THOSE), so the G entries
+// r .. r+G-1 at the cursor sit in G different lanes, in registers.  One round classifies all of them at once (CONT ->
+// keep, STOP -> drop, neither -> needs an evaluation), compacts the entries in front of the first one that needs an
+// evaluation with a vote and a prefix count, and hands that one to the whole group, which evaluates and commits it
+// exactly as before.  Entries behind it are not consumed: they stay in their lanes and are classified again, against
+// the planes as the commit left them, in the next round - so every entry is tested against precisely the memo state
+// the sequential walk would have shown it, and the compacted list, the state and the step count are identical.
+// In-place compaction is safe: a kept entry goes to a position <= its own, positions below the cursor are never read
+// again in this walk, and every lane holds its entry in a register before any lane stores (the vote sits in between).
+template <bool FWD, int G>
+STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
+                                 int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
+                                 int& status, int g, int lane0) {
+    const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
+    const Ring cont = C.cont(d), stop = C.stop(d);
+    int32_t* list = FWD ? W.spF : W.spB;
+    (void)g; (void)lane0;
+    if (skip) nlist = 0;
+    int r = 0, w = 0;
+#if defined(__CUDA_ARCH__)
+    const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const unsigned gm = gbits << lane0;                       // the lanes of this group
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(C.ring);
+#pragma unroll 1
+    for (int k = 0; k < STO_LIST_RING; ++k) {
+        const int e = g + G * k;
+        if (e < nlist)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)(k * C.ring_stride)),
+                         "l"(list + at(e, ld, b)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int mine = g, fetched = 0, cur = 0;   // list index of the entry this lane holds; how many it has taken from its ring
+#define STO_VEC_FETCH()                                                                                               \
+    {                                                                                                                 \
+        asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");                                   \
+        const int slot_ = (fetched & (STO_LIST_RING - 1)) * C.ring_stride;                                            \
+        cur = C.ring[slot_];                                                                                          \
+        if (mine + G * STO_LIST_RING < nlist)                                                                         \
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot_),             \
+                         "l"(list + at(mine + G * STO_LIST_RING, ld, b)) : "memory");                                 \
+        asm volatile("cp.async.commit_group;" ::: "memory");                                                          \
+        ++fetched;                                                                                                    \
+    }
+    if (mine < nlist) STO_VEC_FETCH()
+#endif
+    for (;;) {
+        bool pending = false;
+        int ivf = 0;
+        while (r < nlist) {
+#if defined(__CUDA_ARCH__)
+            const bool valid = mine < nlist;
+            int p = valid ? (FWD ? cur + s : cur - s) : 0;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            const bool c0 = cont.test(p), s0 = stop.test(p);   // two independent shared-memory reads
+            const bool c = valid && c0;
+            const bool pe = valid && !c0 && !s0;
+            const int rot = r & (G - 1);                       // lane (rot + k) mod G holds entry r + k
+            unsigned bc = (__ballot_sync(gm, c) >> lane0) & gbits, bp = (__ballot_sync(gm, pe) >> lane0) & gbits;
+            if (rot) {                                         // bit k = entry r + k
+                bc = ((bc >> rot) | (bc << (G - rot))) & gbits;
+                bp = ((bp >> rot) | (bp << (G - rot))) & gbits;
+            }
+            const int left = nlist - r, nv = (left < G) ? left : G;
+            const int k = mine - r;                            // 0 .. G-1
+            const int f = bp ? (__ffs(bp) - 1) : nv;           // entries in front of the first one to evaluate
+            const unsigned keep = bc & ((1u << f) - 1u);
+            if (k < f && c) {
+                const int dst = w + __popc(keep & ((1u << k) - 1u));
+                if (dst != mine) list[at(dst, ld, b)] = cur;
+            }
+            w += __popc(keep);
+            const int used = f + (bp ? 1 : 0);
+            if (bp) {
+                pending = true;
+                ivf = __shfl_sync(gm, cur, lane0 + ((rot + f) & (G - 1)));
+            }
+            steps += used;
+            r += used;
+            if (k < used) {
+                mine += G;
+                if (mine < nlist) STO_VEC_FETCH()
+            }
+            if (pending) break;
+#else
+            // host emulation of the G lanes: classify the G entries at the cursor against the planes as they stand
+            const int left = nlist - r, nv = (left < G) ? left : G;
+            int ivs[G], f = nv;
+            bool cs[G];
+            for (int k = 0; k < nv; ++k) {
+                ivs[k] = list[at(r + k, ld, b)];
+                int p = FWD ? ivs[k] + s : ivs[k] - s;
+                if (p >= N) p -= N;
+                if (p < 0) p += N;
+                cs[k] = cont.test(p);
+                if (!cs[k] && !stop.test(p) && f == nv) f = k;
+            }
+            for (int k = 0; k < f; ++k)
+                if (cs[k]) { if (w != r + k) list[at(w, ld, b)] = ivs[k]; ++w; }
+            const bool has = f < nv;
+            if (has) { pending = true; ivf = ivs[f]; }
+            steps += f + (has ? 1 : 0);
+            r += f + (has ? 1 : 0);
+            if (pending) break;
+#endif
+        }
+        if (!warp_any(pending)) break;
+        if (pending) {
+            int p = FWD ? ivf + s : ivf - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+            bool changed = false, spawn = false;
+            const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+            if (spawn) { memo_spawn(A, W, b, q, s, nB, nnew, status); ++nnew; }
+            if (!stopped) { if (w != r - 1) list[at(w, ld, b)] = ivf; ++w; }
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#undef STO_VEC_FETCH
+    __syncwarp();   // entries stored by one lane are read by another in the next walk
+#endif
+    return w;
+}
+
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
 template <int G>
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
@@ -886,7 +1015,9 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #else
             // forward re-spawned fronts mostly conflict with their list neighbours (1.6 per batch measured): the
             // one-at-a-time walker is cheaper there
-            wF = memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
+            wF = (G > 1)
+                ? memo_spawned_rows_vec<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
+                : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
 #endif
         }
         STO_CLK(4)
