@@ -223,16 +223,10 @@ struct EvalRes {
     double v_new, a_new;
 };
 
-STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool fwd, int p, int q, double lat0) {
-    const int N = A.N;
-    // both 32-byte records are fetched up front (adjacent in memory): one overlapped round trip per evaluation
-    const double* rec = A.rec + (size_t)b * N * 4;
-    const double* rp = rec + 4 * (size_t)p;
-    const double* rq = rec + 4 * (size_t)q;
-    const double vp = rp[0], ap = rp[1], ddp = rp[2];
-    const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
-    const double dd = fwd ? ddp : ddq;   // chord between p and q is stored at the lower sample
-    const double gq = gsb_at(A, q);
+// The step itself on values already in registers: source state (vp, ap), target state (vq, aq_old), chord dd, target
+// radius Rq and gravity term gq.
+STO_HD EvalRes eval_core(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq, double aq_old, double dd,
+                         double Rq, double gq, double lat0) {
 #if defined(STO_HOSTSIM_COUNTERS)
     ++g_memo_evals[fwd ? 1 : 0];
 #endif
@@ -256,6 +250,18 @@ STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool
     r.v_new = vi;
     r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;
     return r;
+}
+
+STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool fwd, int p, int q, double lat0) {
+    const int N = A.N;
+    // both 32-byte records are fetched up front (adjacent in memory): one overlapped round trip per evaluation
+    const double* rec = A.rec + (size_t)b * N * 4;
+    const double* rp = rec + 4 * (size_t)p;
+    const double* rq = rec + 4 * (size_t)q;
+    const double vp = rp[0], ap = rp[1], ddp = rp[2];
+    const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
+    const double dd = fwd ? ddp : ddq;   // chord between p and q is stored at the lower sample
+    return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);
 }
 
 // Commits an outcome: state write, memo invalidation, the edge's own memo.  Returns true when the front stops.
@@ -427,6 +433,75 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
         }
         STO_SUBCLK(1)
     }
+}
+
+// Outer iteration 0, forward sub-pass over the original rows, rows 0 .. N-2: one dense sequential sweep (front i sits at
+// sample i, every front is live, no forward memo exists yet, so every row is evaluated, in row order, each reading the
+// sample its predecessor may just have written).  That is 2,895 of a Monza line's ~5,500 forward evaluations - 15 % of
+// all evaluation rounds - and the general walker pays a search, two record fetches and six plane read-modify-writes for
+// each.  Here the source state travels in registers, the target record is requested one row ahead, and the plane bits of
+// a 64-row word are collected in registers and stored once: the same evaluations (eval_core) in the same order with the
+// same commits, so state, memos and step count equal memo_original_rows<true>'s.  Per row i (p = i, q = i + 1):
+//   STOP          stop(F)[p] = 1, the front dies;
+//   WRITE / KEEP  cont(F)[p] = 1; on WRITE the target record changes and the backward memos that read it, bits q and
+//                 q + 1 of cont(B) / stop(B), are forgotten (the forward bits memo_invalidate would clear - p, re-set by
+//                 the own edge, and q - are still 0: nothing forward has been recorded at or beyond q).
+// The last row (N-1 -> 0, the seam) is left to the general walker, which finds it as the only dirty front.
+STO_HD void memo_forward_sweep0(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
+                                double lat0, int& nlive, int64_t& steps, int& status) {
+    const int N = A.N, NW = W.W;
+    double* rec = A.rec + (size_t)b * N * 4;
+    const Ring live = C.live(1), cont = C.cont(1), stop = C.stop(1), cb = C.cont(0), sb = C.stop(0);
+    double vp = rec[0], ap = rec[1], ddp = rec[2];
+    double nv = rec[4], na = rec[5], nd = rec[6], nR = rec[7];   // record of sample 1, then always one row ahead
+    u64 clr = 0, clr_next = 0;   // backward memo bits to forget: this word, the next one
+    bool wrap0 = false;
+    for (int w = 0; w < NW; ++w) {
+        const int i0 = 64 * w;
+        const int n = (N - 1 - i0 < 64) ? (N - 1 - i0) : 64;   // rows i0 .. i0+n-1 (all <= N-2)
+        u64 contw = 0, stopw = 0;
+        for (int t = 0; t < n; ++t) {
+            const int q = i0 + t + 1;
+            const double vq = nv, aq_old = na, ddq = nd, Rq = nR;
+            if (q + 1 < N) {
+                const double* rn = rec + 4 * (size_t)(q + 1);
+                nv = rn[0]; na = rn[1]; nd = rn[2]; nR = rn[3];
+            }
+            const EvalRes r = eval_core(V, true, vp, ap, vq, aq_old, ddp, Rq, gsb_at(A, q), lat0);
+#if defined(STO_HOSTSIM_COUNTERS)
+            if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(i0 + t); g_log.push_back(r.kind); }
+#endif
+            if (r.kind == EV_WRITE || r.kind == EV_KEEP) {
+                contw |= 1ull << t;
+                if (r.kind == EV_WRITE) {
+                    rec[4 * (size_t)q + 0] = r.v_new;
+                    rec[4 * (size_t)q + 1] = r.a_new;
+                    const int bq = t + 1, b1 = t + 2;              // bits of q and q + 1 relative to this word
+                    if (bq < 64) clr |= 1ull << bq; else clr_next |= 1ull << (bq - 64);
+                    if (q + 1 == N) wrap0 = true;
+                    else if (b1 < 64) clr |= 1ull << b1;
+                    else clr_next |= 1ull << (b1 - 64);
+                }
+                vp = r.v_new; ap = r.a_new;                        // KEEP: bit-identical to what q holds
+            } else {                                               // EV_STOP, or EV_ZERO (the reference raises)
+                if (r.kind == EV_ZERO) status |= STO_CAND_ZERO_SPEED; else stopw |= 1ull << t;
+                --nlive;
+                ++steps;                                           // (the fronts that go on are counted by the general walker)
+                vp = vq; ap = aq_old;
+            }
+            ddp = ddq;
+        }
+        if (n > 0) {
+            const u64 m = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+            live.set_word(w, (live.word(w) & ~m) | contw);
+            cont.set_word(w, (cont.word(w) & ~m) | contw);
+            stop.set_word(w, (stop.word(w) & ~m) | stopw);
+        }
+        if (clr) { cb.set_word(w, cb.word(w) & ~clr); sb.set_word(w, sb.word(w) & ~clr); }
+        clr = clr_next;
+        clr_next = 0;
+    }
+    if (wrap0) { cb.clear(0); sb.clear(0); }
 }
 
 // ---- lane groups -------------------------------------------------------------------------------------------------
@@ -818,10 +893,11 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
 template <bool FWD, int G>
 STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                                  int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
-                                 int& status, int g, int lane0) {
+                                 int& status, int g, int lane0 STO_SUB_PARAM) {
     const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
     const Ring cont = C.cont(d), stop = C.stop(d);
     int32_t* list = FWD ? W.spF : W.spB;
+    STO_SUBCLK_DECL
     (void)g; (void)lane0;
     if (skip) nlist = 0;
     int r = 0, w = 0;
@@ -912,8 +988,11 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
             if (pending) break;
 #endif
         }
+        STO_SUBCLK(2)
         if (!warp_any(pending)) break;
+        STO_SUBCNT(6)
         if (pending) {
+            STO_SUBCNT(5)
             int p = FWD ? ivf + s : ivf - s;
             if (p >= N) p -= N;
             if (p < 0) p += N;
@@ -923,6 +1002,7 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
             if (spawn) { memo_spawn(A, W, b, q, s, nB, nnew, status); ++nnew; }
             if (!stopped) { if (w != r - 1) list[at(w, ld, b)] = ivf; ++w; }
         }
+        STO_SUBCLK(3)
     }
 #if defined(__CUDA_ARCH__)
 #undef STO_VEC_FETCH
@@ -1001,6 +1081,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         STO_LOG_PHASE(2)
         {
             int none = 0;  // forward steps never spawn (simulator.py:340 cannot hold)
+            if (iters == 0 && !done && nliveF == N) memo_forward_sweep0(A, W, C, V, b, lat0, nliveF, steps, status);
             memo_original_rows<true>(A, W, C, V, b, done || nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status STO_SUB_ARG);
         }
         STO_CLK(3)
@@ -1016,7 +1097,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             // forward re-spawned fronts mostly conflict with their list neighbours (1.6 per batch measured): the
             // one-at-a-time walker is cheaper there
             wF = (G > 1)
-                ? memo_spawned_rows_vec<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
+                ? memo_spawned_rows_vec<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0 STO_SUB_ARG)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
 #endif
         }
