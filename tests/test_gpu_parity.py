@@ -132,6 +132,31 @@ def test_qss_against_oracle_and_reference(sto, name, impl):
     assert abs(float(res["summary"][0, 0]) - d["result_scalars"][0]) < 1e-13   # total_time quirk (= TIME[0])
 
 
+@pytest.mark.gpu
+def test_qss_memo_word_boundaries(sto):
+    """Track sizes around multiples of 64 (plane word size), 8 different lines per size so that a warp holds lane groups
+    with different lists: the memoised kernel (lane groups, vectorised list walk, dense iteration-0 sweep) against the
+    oracle, bit for bit, including the front-step count."""
+    from spline_trajectory_optimization_b200 import _lib
+    d = golden("sim_s10k3_i2")
+    veh, ov = _lib.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    n_full = len(d["in_X"])
+    for n in (128, 129, 191, 192, 193, 257, 1025):
+        B = 8
+        X, Y, R = np.empty((B, n)), np.empty((B, n)), np.empty((B, n))
+        for c in range(B):
+            idx = (np.linspace(0, n_full - 1, n, endpoint=False).astype(int) + 37 * c) % n_full
+            X[c], Y[c], R[c] = d["in_X"][idx], d["in_Y"][idx], d["in_CURVATURE"][idx] * (1.0 + 0.03 * c)
+        res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=B, sin_bank=np.zeros(n), impl=sto.IMPL["memo"])
+        torch.cuda.synchronize()
+        assert not res["status"][:B].cpu().numpy().any()
+        for c in range(B):
+            o = O.qss(X[c], Y[c], R[c], np.zeros(n), ov, 0)
+            assert np.array_equal(res["speed"][:, c].cpu().numpy(), o["v"]), (n, c)
+            assert np.array_equal(res["time"][:, c].cpu().numpy(), o["time"]), (n, c)
+            assert float(res["lap"][c]) == o["lap"] and float(res["summary"][6, c]) == o["steps"], (n, c)
+
+
 @pytest.mark.parametrize("impl", ["plain", "memo"])
 def test_qss_synthetic_tables(sto, impl):
     """Infinite turn radius, banked samples, N = 8 / 64 / 257 (tiny N runs the plain kernel under 'memo')."""

@@ -96,6 +96,25 @@ def test_qss_lane_group_emulation_bit_exact(name, group):
     assert r["lap"][0] == o["lap"] and r["summary"][0, 6] == o["steps"]
 
 
+@pytest.mark.parametrize("n", [128, 129, 191, 192, 193, 256, 257, 321, 1024, 1025])
+def test_qss_memo_word_boundaries(n):
+    """Track sizes around multiples of 64 (the bit planes' word size): the dense iteration-0 forward sweep collects plane
+    bits per word and leaves the seam row to the general walker; the list walkers own entries modulo the group size.
+    One lane per candidate and emulated lane groups against the oracle, bit for bit, including the step count."""
+    d = golden("sim_s10k3_i2")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    idx = np.linspace(0, len(d["in_X"]) - 1, n, endpoint=False).astype(int)
+    x, y, r = d["in_X"][idx].copy(), d["in_Y"][idx].copy(), d["in_CURVATURE"][idx].copy()
+    sb = np.zeros(n)
+    o = O.qss(x, y, r, sb, ov, 0)
+    for impl in (1, 104, 108):
+        h = H.qss(impl, x[None], y[None], r[None], sb, hv)
+        assert h["status"][0] == 0
+        for k in ("v", "a", "lat", "time"):
+            assert np.array_equal(h[k][0], o[k]), (impl, k)
+        assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
+
+
 @pytest.mark.parametrize("split", [2, 7, 16])
 def test_eval_sample_range_split(split):
     """Splitting a candidate's samples over lanes (eval_range) gives the same bits as one walk over all of them,
