@@ -511,14 +511,18 @@ STO_HD void memo_forward_sweep0(const QssArgs& A, const MemoWork& W, const MemoC
 // (bar the seam, which sits in another word).  So up to G consecutive dirty fronts of a word are evaluated at once,
 // one per lane, against the state as it stood, and committed in row order - bit-identical to doing them one by one,
 // G times shorter on the critical path.  (Dirty backward fronts cluster: half of them sit in words with >= 15.)
+// (rolled on purpose: unrolled G times they were 390 instructions of the backward walker's code, and the kernel is
+//  bound by instruction fetch - profiles/r01_qss_memo_s4_ncu_summary.txt)
 STO_HD int kth_bit(u64 x, int k) {
+#pragma unroll 1
     for (int i = 0; i < k; ++i) x &= x - 1ull;
     return ctz64(x);
 }
 STO_HD u64 lowest_bits(u64 x, int k) {
-    u64 m = 0;
-    for (int i = 0; i < k; ++i) { const u64 low = x & (~x + 1ull); m |= low; x ^= low; }
-    return m;
+    const u64 x0 = x;
+#pragma unroll 1
+    for (int i = 0; i < k; ++i) x &= x - 1ull;   // x0 without its k lowest set bits
+    return x0 ^ x;
 }
 
 template <int G>
@@ -903,7 +907,6 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
     int r = 0, w = 0;
 #if defined(__CUDA_ARCH__)
     const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-    const unsigned gm = gbits << lane0;                       // the lanes of this group
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(C.ring);
 #pragma unroll 1
     for (int k = 0; k < STO_LIST_RING; ++k) {
@@ -930,9 +933,14 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
     for (;;) {
         bool pending = false;
         int ivf = 0;
-        while (r < nlist) {
 #if defined(__CUDA_ARCH__)
-            const bool valid = mine < nlist;
+        // The groups of a warp search in lock step (a group that has found its front, or finished its list, idles with
+        // its predicates down - it would wait at the vote below anyway): every vote and shuffle is then a single
+        // full-mask instruction instead of a partial-mask helper call.
+        for (;;) {
+            const bool searching = !pending && r < nlist;
+            if (!warp_any(searching)) break;
+            const bool valid = searching && mine < nlist;
             int p = valid ? (FWD ? cur + s : cur - s) : 0;
             if (p >= N) p -= N;
             if (p < 0) p += N;
@@ -940,33 +948,35 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
             const bool c = valid && c0;
             const bool pe = valid && !c0 && !s0;
             const int rot = r & (G - 1);                       // lane (rot + k) mod G holds entry r + k
-            unsigned bc = (__ballot_sync(gm, c) >> lane0) & gbits, bp = (__ballot_sync(gm, pe) >> lane0) & gbits;
+            unsigned bc = (__ballot_sync(0xffffffffu, c) >> lane0) & gbits;
+            unsigned bp = (__ballot_sync(0xffffffffu, pe) >> lane0) & gbits;
             if (rot) {                                         // bit k = entry r + k
                 bc = ((bc >> rot) | (bc << (G - rot))) & gbits;
                 bp = ((bp >> rot) | (bp << (G - rot))) & gbits;
             }
-            const int left = nlist - r, nv = (left < G) ? left : G;
-            const int k = mine - r;                            // 0 .. G-1
+            const int left = nlist - r, nv = (left < G) ? ((left > 0) ? left : 0) : G;
+            const int k = mine - r;                            // 0 .. G-1 while searching
             const int f = bp ? (__ffs(bp) - 1) : nv;           // entries in front of the first one to evaluate
-            const unsigned keep = bc & ((1u << f) - 1u);
-            if (k < f && c) {
+            const unsigned keep = bc & ((f >= 32) ? 0xffffffffu : ((1u << f) - 1u));
+            if (valid && k < f && c) {
                 const int dst = w + __popc(keep & ((1u << k) - 1u));
                 if (dst != mine) list[at(dst, ld, b)] = cur;
             }
-            w += __popc(keep);
-            const int used = f + (bp ? 1 : 0);
-            if (bp) {
-                pending = true;
-                ivf = __shfl_sync(gm, cur, lane0 + ((rot + f) & (G - 1)));
+            const int got = __shfl_sync(0xffffffffu, cur, lane0 + ((rot + f) & (G - 1)));
+            if (searching) {
+                w += __popc(keep);
+                const int used = f + (bp ? 1 : 0);
+                if (bp) { pending = true; ivf = got; }
+                steps += used;
+                r += used;
+                if (k < used) {
+                    mine += G;
+                    if (mine < nlist) STO_VEC_FETCH()
+                }
             }
-            steps += used;
-            r += used;
-            if (k < used) {
-                mine += G;
-                if (mine < nlist) STO_VEC_FETCH()
-            }
-            if (pending) break;
+        }
 #else
+        while (r < nlist) {
             // host emulation of the G lanes: classify the G entries at the cursor against the planes as they stand
             const int left = nlist - r, nv = (left < G) ? left : G;
             int ivs[G], f = nv;
@@ -986,8 +996,8 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
             steps += f + (has ? 1 : 0);
             r += f + (has ? 1 : 0);
             if (pending) break;
-#endif
         }
+#endif
         STO_SUBCLK(2)
         if (!warp_any(pending)) break;
         STO_SUBCNT(6)
@@ -1074,9 +1084,13 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             memo_original_rows<false>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status STO_SUB_ARG);
         STO_CLK(1)
         STO_LOG_PHASE(1)
-        const int wB = (G > 1)
-            ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0)
-            : memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
+        // (a list walker nobody in the warp has work for is not entered at all: the kernel is bound by instruction
+        //  fetch and every walker is ~15 KB of code)
+        int wB = 0;
+        if (warp_any(!done && nB > 0))
+            wB = (G > 1)
+                ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0)
+                : memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
         STO_LOG_PHASE(2)
         {
@@ -1086,8 +1100,8 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         }
         STO_CLK(3)
         STO_LOG_PHASE(3)
-        int wF;
-        {
+        int wF = 0;
+        if (warp_any(!done && nF > 0)) {
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
 #if defined(STO_GROUP_SF)
             wF = (G > 1)
