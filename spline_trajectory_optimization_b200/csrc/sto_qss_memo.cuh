@@ -758,6 +758,55 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
 #endif
     for (;;) {
         int cnt = 0;
+#if defined(__CUDA_ARCH__)
+        // Collection in warp lock step: lane k of the group keeps member k (its sample and reserved slot) in registers and
+        // tests the entry at the cursor against IT; one full-mask vote tells the group whether any member conflicts.  (The
+        // G-way compare / select chains this replaces were ~1,000 cycles per list entry: tools/phase_profile.py.)
+        int my_p = -1, my_slot = -1;
+        bool closed = false;                                   // the batch ended at a conflicting entry (kept in `held`)
+        for (;;) {
+            const bool act = !closed && cnt < G && (held != -2 || r < nlist);
+            if (!warp_any(act)) break;
+            int iv = -1;
+            if (act) {
+                if (held != -2) { iv = held; held = -2; }
+                else {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(STO_LIST_RING - 1) : "memory");
+                    const int slot = (r & (STO_LIST_RING - 1)) * C.ring_stride;
+                    iv = C.ring[slot];
+                    if (r + STO_LIST_RING < nlist)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + 4u * (unsigned)slot),
+                                     "l"(list + at(r + STO_LIST_RING, ld, b)) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    ++r;
+                }
+            }
+            const bool have = act && iv >= 0;                  // (iv < 0: tombstone of an earlier walk)
+            int p = have ? (FWD ? iv + s : iv - s) : 0;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            bool hit = false;
+            if (have && g < cnt) {
+                if (FWD) { const int pa1 = (my_p + 1 == N) ? 0 : my_p + 1; hit = p == my_p || p == pa1; }
+                else { const int pam = (my_p == 0) ? N - 1 : my_p - 1; hit = p == pam; }
+            }
+            const bool conflict = ((__ballot_sync(0xffffffffu, hit) >> lane0) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))) != 0u;
+            if (have) {
+                if (conflict) { held = iv; closed = true; }
+                else {
+                    ++steps;
+                    const bool c0 = cont.test(p), s0 = stop.test(p);
+                    if (c0) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; }
+                    else if (!s0) {
+                        if (g == cnt) { my_p = p; my_slot = w; }
+                        if (w != r - 1) list[at(w, ld, b)] = iv;   // slot reserved; a tombstone replaces it if the front stops
+                        ++w;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+#else
         int pend_p[G], pend_slot[G];
 #pragma unroll
         for (int k = 0; k < G; ++k) { pend_p[k] = -1; pend_slot[k] = -1; }
@@ -802,15 +851,13 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
             ++w;
             ++cnt;
         }
+#endif
         if (!warp_any(cnt > 0)) break;
 #if defined(STO_HOSTSIM_COUNTERS)
         g_sp_evals[d] += cnt; ++g_sp_changed[d];   // (re-used here: evaluations / batches of the group walker)
 #endif
 #if defined(__CUDA_ARCH__)
-        int p = -1, slot = -1;
-#pragma unroll
-        for (int k = 0; k < G; ++k)
-            if (k == g) { p = pend_p[k]; slot = pend_slot[k]; }
+        const int p = my_p, slot = my_slot;
         const bool has = g < cnt;
         const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
         EvalRes res;
