@@ -190,6 +190,29 @@ STO_HD void memo_invalidate(const MemoCtx& C, int j, int N) {
     clear_pair(C.stop(1), jp, j);
 }
 
+// memo_invalidate(q) followed by "the own edge p -> q is CONT" (apply_res, a step that changed q and goes on), in four
+// read-modify-writes instead of six: in the own direction the pair memo_invalidate clears is {p, q}, so CONT ends as
+// "q cleared, p set" and STOP as "both cleared"; the other direction's pair is cleared as before.
+STO_HD void memo_invalidate_cont(const MemoCtx& C, int p, int q, int d, int N) {
+    const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
+    const Ring co = C.cont(d), so = C.stop(d);
+    if ((p >> 6) == (q >> 6)) {
+        u64* wd = co.m + (size_t)(p >> 6) * co.stride;
+        *wd = (*wd & ~(1ull << (q & 63))) | (1ull << (p & 63));
+    } else {
+        co.clear(q);
+        co.set(p);
+    }
+    clear_pair(so, p, q);
+    if (d) {   // forward step: the backward edges that read q are q -> q-1 and q+1 -> q
+        clear_pair(C.cont(0), q, qn);
+        clear_pair(C.stop(0), q, qn);
+    } else {   // backward step: the forward edges that read q are q -> q+1 and q-1 -> q
+        clear_pair(C.cont(1), qp, q);
+        clear_pair(C.stop(1), qp, q);
+    }
+}
+
 // front_step<FWD> of sto_qss.cuh with the direction as a run-time value (lanes of one warp may be in different
 // sub-passes): the same operations on the same operands, selected instead of branched, so results are bit-identical.
 STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double dd, double Rq,
@@ -273,11 +296,19 @@ STO_HD bool apply_res(const QssArgs& A, const MemoCtx& C, int b, bool fwd, int p
 #if defined(STO_HOSTSIM_COUNTERS)
     if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(p); g_log.push_back(r.kind); }
 #endif
+    if (r.kind == EV_WRITE) {   // the common changing step: state write, invalidation and own-edge memo fused
+        double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
+        rq[0] = r.v_new;
+        rq[1] = r.a_new;
+        memo_invalidate_cont(C, p, q, d, N);
+        changed = true;
+        return false;
+    }
     switch (r.kind) {
         case EV_KILL: return true;
         case EV_ZERO: status |= STO_CAND_ZERO_SPEED; return true;
         case EV_STOP: C.stop(d).set(p); C.cont(d).clear(p); return true;
-        case EV_WRITE: case EV_SPAWN: {
+        case EV_SPAWN: {
             double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
             rq[0] = r.v_new;
             rq[1] = r.a_new;
@@ -287,7 +318,7 @@ STO_HD bool apply_res(const QssArgs& A, const MemoCtx& C, int b, bool fwd, int p
         }
         default: break;
     }
-    if (r.kind == EV_WRITE || r.kind == EV_KEEP) {
+    if (r.kind == EV_KEEP) {
         C.cont(d).set(p);  // re-running this step on the state as it now stands rewrites the same values
         C.stop(d).clear(p);
         return false;
@@ -429,7 +460,11 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
             // edge -> re-read the window.  Backward: row i writes the sample row i-1 has already left; the one later
             // row it can reach is the seam (row 0 writes what row N-1 reads), which lives in the last word, whose
             // window is only formed when the walk gets there (N >= 128: never word 0).
-            att = (changed && FWD) ? (L & ~cont.window(start) & ~donemask) : (att & ~donemask);
+            // (the only memo bit above t this commit can have touched is t + 1 - the edge out of the sample just
+            //  written, cleared by the invalidation - so the window need not be re-read: row t + 1 is dirty now if it
+            //  is live; t = 63: that row belongs to the next word, whose window is formed when the walk gets there)
+            att &= ~donemask;
+            if (changed && FWD) att |= L & (bit << 1);
         }
         STO_SUBCLK(1)
     }
