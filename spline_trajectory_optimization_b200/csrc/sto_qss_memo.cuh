@@ -1103,6 +1103,81 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
     return w;
 }
 
+#if defined(__CUDA_ARCH__)
+// qss_finish for a lane group: one lane walking N records with two divisions per sample was 4.6 % of the kernel
+// (tools/phase_profile.py).  The lanes take samples g, g + G, ... (lateral acceleration, segment time, outputs, extrema -
+// min / max do not depend on the order), park each segment time in the record's radius slot, which nobody reads any
+// more, and lane 0 then adds them up in sample order: the same operations, the same sum order, the same lap.
+template <int G>
+STO_D void qss_finish_group(const QssArgs& A, double* rec, int b, bool active, int status, int64_t steps, int iters,
+                            int g, int lane0) {
+    const int N = A.N, ld = A.ld;
+    const unsigned full = 0xffffffffu;
+    double vmin = 0.0, vmaxs = 0.0, latmax = 0.0, amax = 0.0, amin = 0.0;
+    bool bad = false, first = true;
+    const bool ok = active && status == 0;
+    if (ok) {
+        for (int i = g; i < N; i += G) {
+            const double vi = rec[4 * (size_t)i + 0], ai = rec[4 * (size_t)i + 1], Ri = rec[4 * (size_t)i + 3];
+            const double li = calc_lat(vi, Ri, gsb_at(A, i));
+            if (A.lat) A.lat[at(i, ld, b)] = li;
+            if (A.v) A.v[at(i, ld, b)] = vi;
+            if (A.a) A.a[at(i, ld, b)] = ai;
+            if (first) { vmin = vmaxs = vi; latmax = li; amax = amin = ai; first = false; }
+            else {
+                vmin = (vi < vmin) ? vi : vmin;
+                vmaxs = (vi > vmaxs) ? vi : vmaxs;
+                latmax = (li > latmax) ? li : latmax;
+                amax = (ai > amax) ? ai : amax;
+                amin = (ai < amin) ? ai : amin;
+            }
+            bad = bad || !(vi == vi);
+            // TIME[i + 1] = segment i -> i + 1; TIME[0] = the closing segment N-1 -> 0 (trajectory.py:158-180)
+            const int in = (i + 1 == N) ? 0 : i + 1;
+            const double t = A.df[at(i, ld, b)] / (0.5 * (vi + rec[4 * (size_t)in + 0]));
+            if (A.tseg) A.tseg[at(in, ld, b)] = t;
+            bad = bad || !(t == t);
+            rec[4 * (size_t)i + 3] = t;
+        }
+    }
+    __syncwarp();
+    // extrema and the NaN flag across the group (every lane of a group of <= N / 128 lanes has seen a sample)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double v1 = __shfl_xor_sync(full, vmin, o), v2 = __shfl_xor_sync(full, vmaxs, o);
+        const double l1 = __shfl_xor_sync(full, latmax, o), a1 = __shfl_xor_sync(full, amax, o), a2 = __shfl_xor_sync(full, amin, o);
+        vmin = (v1 < vmin) ? v1 : vmin;
+        vmaxs = (v2 > vmaxs) ? v2 : vmaxs;
+        latmax = (l1 > latmax) ? l1 : latmax;
+        amax = (a1 > amax) ? a1 : amax;
+        amin = (a2 < amin) ? a2 : amin;
+    }
+    const unsigned gbits = (G == 32) ? full : ((1u << G) - 1u);
+    if ((__ballot_sync(full, bad) >> lane0) & gbits) status |= STO_CAND_NAN;
+    if (!active || g != 0) return;
+    double lap, t0 = 0.0;
+    if (ok) {
+        t0 = rec[4 * (size_t)(N - 1) + 3];
+        lap = 0.0 + t0;
+        for (int i = 0; i + 1 < N; ++i) lap = lap + rec[4 * (size_t)i + 3];
+    } else {
+        lap = nan("");
+    }
+    A.lap[b] = lap;
+    if (A.status) A.status[b] |= status;
+    if (A.summary) {
+        A.summary[at(0, ld, b)] = t0;
+        A.summary[at(1, ld, b)] = vmin;
+        A.summary[at(2, ld, b)] = vmaxs;
+        A.summary[at(3, ld, b)] = latmax;
+        A.summary[at(4, ld, b)] = amax;
+        A.summary[at(5, ld, b)] = amin;
+        A.summary[at(6, ld, b)] = (double)steps;
+        A.summary[at(7, ld, b)] = (double)iters;
+    }
+}
+#endif
+
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
 template <int G>
 STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
@@ -1218,7 +1293,12 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         STO_CLK(5)
     }
     STO_CLK(6)
+#if defined(__CUDA_ARCH__)
+    if (G > 1) qss_finish_group<G>(A, A.rec + (size_t)b * N * 4, b, active, status, steps, iters, g, lane0);
+    else if (active) qss_finish(A, StateRec{A.rec + (size_t)b * N * 4}, true, b, status, steps, iters);
+#else
     if (active && g == 0) qss_finish(A, StateRec{A.rec + (size_t)b * N * 4}, true, b, status, steps, iters);
+#endif
     STO_CLK(7)
 #if defined(STO_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (active && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)dbg_acc[k];
