@@ -1273,9 +1273,34 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #endif
         }
         STO_CLK(4)
+        if (!done && wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
+#if defined(__CUDA_ARCH__)
+        if (G > 1) {
+            // the fold below, G rows at a time (one per lane; the serial loop was a chain of dependent global round trips,
+            // 2.5 % of the kernel).  The move is in place and downwards (wB <= nB): a wave reads its G entries, the warp
+            // synchronises, then it writes - positions a later wave reads lie above everything written so far.
+            const int todo = done ? 0 : nnew;
+            for (int j0 = 0; warp_any(j0 < todo); j0 += G) {
+                const int j = j0 + g;
+                const bool mine = j < todo;
+                const int ivb = mine ? W.spB[at(nB + j, ld, b)] : 0;   // (q + s + 1) mod N
+                __syncwarp();
+                if (mine) {
+                    int ivf = ivb - 2 * (s + 1);                        // (q - (s + 1)) mod N: in [-2N, N)
+                    if (ivf < 0) ivf += N;
+                    if (ivf < 0) ivf += N;
+                    W.spB[at(wB + j, ld, b)] = ivb;
+                    W.spF[at(wF + j, ld, b)] = ivf;
+                }
+            }
+            __syncwarp();   // the next iteration's walkers read entries stored by other lanes
+        }
+#endif
         if (!done) {
             // fold the rows spawned in this iteration behind both lists (simulator.py:351-356)
-            if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
+#if defined(__CUDA_ARCH__)
+            if (G == 1)
+#endif
             for (int j = 0; j < nnew; ++j) {
                 const int ivb = W.spB[at(nB + j, ld, b)];   // (q + s + 1) mod N
                 int ivf = ivb - 2 * (s + 1);                  // (q - (s + 1)) mod N: in [-2N, N), no integer division
