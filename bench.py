@@ -336,9 +336,9 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": "qss_%s_kernel" % args.qss, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one qss_memo_kernel<8> launch at this
-                         # workload, from profiles/r01_qss_memo_s4_ncu_summary.txt (ncu --set full); not live
-                         "traffic": (3.884e9 if (args.qss == "memo" and B == CANDIDATES_PER_GPU) else None),
-                         "traffic_source": "ncu --set full capture, profiles/r01_qss_memo_s4_ncu_summary.txt",
+                         # workload, from profiles/r01_qss_memo_s5_ncu_summary.txt (ncu --set full); not live
+                         "traffic": (4.290e9 if (args.qss == "memo" and B == CANDIDATES_PER_GPU) else None),
+                         "traffic_source": "ncu --set full capture, profiles/r01_qss_memo_s5_ncu_summary.txt",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_candidate": 8 * M + 8, "kernel_ms": qss_ms,
                          "stage_ms": {"status": float(stage_ms[0]), "fit": float(stage_ms[1]),
