@@ -66,3 +66,24 @@ def to_sm(a_cm, device="cuda"):
 
 def to_cm(t_sm, B):
     return t_sm[:, :B].T.contiguous().cpu().numpy()
+
+
+def synthetic_closed_track(seed, n):
+    """A closed line at ~2 m spacing from a piecewise-constant curvature (straights, sweepers, hairpins down to R = 8 m,
+    optionally banked): many braking zones, re-initialisations and re-spawned rows on a few hundred samples."""
+    rng = np.random.default_rng(seed)
+    kappa = np.zeros(n)
+    i = 0
+    while i < n:
+        L = int(rng.integers(5, 60))
+        kind = rng.random()
+        k = 0.0 if kind < 0.35 else (rng.normal(0, 0.01) if kind < 0.8 else rng.choice([-1, 1]) * rng.uniform(0.03, 0.12))
+        kappa[i:i + L] = k
+        i += L
+    kappa += (2 * np.pi / (2.0 * n) - kappa.mean())
+    psi = np.cumsum(kappa * 2.0)
+    x, y = np.cumsum(2.0 * np.cos(psi)), np.cumsum(2.0 * np.sin(psi))
+    with np.errstate(divide="ignore"):
+        R = np.where(np.abs(kappa) > 1e-9, 1.0 / np.abs(kappa), np.inf)
+    bank = rng.uniform(-0.05, 0.1, n) * (rng.random() < 0.5)
+    return x, y, R, np.sin(bank)

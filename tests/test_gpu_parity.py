@@ -157,6 +157,28 @@ def test_qss_memo_word_boundaries(sto):
             assert float(res["lap"][c]) == o["lap"] and float(res["summary"][6, c]) == o["steps"], (n, c)
 
 
+def test_qss_memo_random_tracks(sto):
+    """Eight different random synthetic tracks per batch (hairpins, banked stretches), three sizes: a warp then holds lane
+    groups with very different lists and round counts.  Memoised kernel against the oracle, bit for bit."""
+    from helpers import synthetic_closed_track
+    from spline_trajectory_optimization_b200 import _lib
+    d = golden("sim_s10k3_i2")
+    veh, ov = _lib.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    for n in (200, 333, 640):
+        B = 8
+        T = [synthetic_closed_track(1000 * n + c, n) for c in range(B)]
+        X, Y, R = (np.stack([t[k] for t in T]) for k in range(3))
+        sb = T[0][3]                                            # the bank profile is shared by a batch
+        res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=B, sin_bank=sb, impl=sto.IMPL["memo"])
+        torch.cuda.synchronize()
+        assert not res["status"][:B].cpu().numpy().any()
+        for c in range(B):
+            o = O.qss(X[c], Y[c], R[c], sb, ov, 0)
+            assert np.array_equal(res["speed"][:, c].cpu().numpy(), o["v"]), (n, c)
+            assert np.array_equal(res["time"][:, c].cpu().numpy(), o["time"]), (n, c)
+            assert float(res["lap"][c]) == o["lap"] and float(res["summary"][6, c]) == o["steps"], (n, c)
+
+
 @pytest.mark.parametrize("impl", ["plain", "memo"])
 def test_qss_synthetic_tables(sto, impl):
     """Infinite turn radius, banked samples, N = 8 / 64 / 257 (tiny N runs the plain kernel under 'memo')."""

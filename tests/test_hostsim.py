@@ -115,6 +115,24 @@ def test_qss_memo_word_boundaries(n):
         assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_qss_memo_random_tracks(seed):
+    """Random synthetic tracks (hairpins, banked stretches, 128-700 samples): the memoised schedule with one lane per line
+    and with emulated lane groups of 2 / 4 / 8 against the oracle, bit for bit, including the step count."""
+    from helpers import synthetic_closed_track
+    d = golden("sim_s10k3_i2")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    n = int(np.random.default_rng(100 + seed).integers(128, 700))
+    x, y, r, sb = synthetic_closed_track(seed, n)
+    o = O.qss(x, y, r, sb, ov, 0)
+    for impl in (1, 102, 104, 108):
+        h = H.qss(impl, x[None], y[None], r[None], sb, hv)
+        assert h["status"][0] == 0
+        for k in ("v", "a", "lat", "time"):
+            assert np.array_equal(h[k][0], o[k]), (impl, k)
+        assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
+
+
 @pytest.mark.parametrize("split", [2, 7, 16])
 def test_eval_sample_range_split(split):
     """Splitting a candidate's samples over lanes (eval_range) gives the same bits as one walk over all of them,
