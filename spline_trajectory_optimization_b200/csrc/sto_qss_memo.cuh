@@ -1265,8 +1265,8 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
                 ? memo_spawned_rows_group<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
 #else
-            // forward re-spawned fronts mostly conflict with their list neighbours (1.6 per batch measured): the
-            // one-at-a-time walker is cheaper there
+            // forward re-spawned fronts mostly conflict with their list neighbours (1.6 evaluations per batch measured),
+            // so they are evaluated one at a time; a lane group spreads the list WALK over its lanes instead
             wF = (G > 1)
                 ? memo_spawned_rows_vec<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0 STO_SUB_ARG)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
