@@ -272,6 +272,28 @@ def test_fit_lsq_flags_empty_knot_interval():
     assert not st.any() and np.isfinite(cx).all()
 
 
+@pytest.mark.parametrize("M,scale", [(700, 1.0), (1500, 1e-3), (4000, 1e3), (5999, 1.0)])
+def test_fit_fitpack_long_lines_decayed_pivots(M, scale):
+    """Long closed lines: the fill-in of the two periodic rows decays by ~0.27 per band row, is below 2^-30 of the diagonal
+    from row ~16 on (fpgivs in its collapsed form, fp_givs_decayed) and denormal from row ~510 on for the rest of the
+    sweep.  Coefficients must still equal SciPy's bit for bit, at any coordinate scale."""
+    import warnings
+    from scipy.interpolate import splprep
+    rng = np.random.default_rng(M)
+    th = np.sort(rng.uniform(0, 2 * np.pi, M))
+    rad = (50 + 400 * rng.random()) * (1 + 0.3 * np.sin(3 * th + rng.random()) + 0.02 * rng.standard_normal(M))
+    pts = np.stack([rad * np.cos(th), 0.6 * rad * np.sin(th)], -1) * scale
+    c = np.vstack([pts, pts[:1]])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        (t, (rx, ry), k), u = splprep([c[:, 0], c[:, 1]], s=0.0, k=3, per=1)
+    hu, hcx, hcy, st = H.fit_points(pts[None], -108)
+    assert not st.any() and np.array_equal(hu[0], u)
+    assert np.array_equal(hcx[0], rx) and np.array_equal(hcy[0], ry)
+    ot, ocx, ocy = O.fit_periodic_cubic(pts)
+    assert np.array_equal(ot, t) and np.array_equal(ocx, rx) and np.array_equal(ocy, ry)
+
+
 def test_fit_fitpack_small_and_random_lines():
     """FITPACK restatement vs SciPy itself (run here as the checker): bit for bit from the smallest closed line
     (M = 3, where the periodic wrap folds back onto the border block) upwards."""
