@@ -161,6 +161,12 @@ void hostsim_att_hist(long long* out32) {
     for (int d = 0; d < 2; ++d) for (int k = 0; k < 16; ++k) { out32[d * 16 + k] = sto::g_att_hist[d][k]; sto::g_att_hist[d][k] = 0; }
 }
 
+// prototype switch + counters of memo_spawned_fwd_batch (analysis tooling)
+void hostsim_fwd_batch(int on) { sto::g_fwd_batch = on; }
+void hostsim_fwd_batch_counters(long long* out4, int reset) {
+    for (int k = 0; k < 4; ++k) { out4[k] = sto::g_fb[k]; if (reset) sto::g_fb[k] = 0; }
+}
+
 void hostsim_counters(long long* out4, int reset) {
     out4[0] = sto::g_memo_evals[0]; out4[1] = sto::g_memo_evals[1];
     out4[2] = sto::g_memo_words[0]; out4[3] = sto::g_memo_words[1];

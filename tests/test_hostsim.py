@@ -133,6 +133,37 @@ def test_qss_memo_random_tracks(seed):
         assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
 
 
+def test_forward_list_batch_prototype_is_exact():
+    """Next-round prototype (host only, memo_spawned_fwd_batch): the forward re-spawned list evaluated up to G fronts at a
+    time, resolved from start-of-segment memo bits plus the members' outcomes, cut where a member writes a later entry's
+    sample.  Must reproduce the one-at-a-time walk bit for bit (state, list, step count); reports evaluations per batch."""
+    import ctypes as C
+    from helpers import synthetic_closed_track
+    L = H.lib()
+    d = golden("sim_s10k3_i2")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    cases = [(d["in_X"], d["in_Y"], d["in_CURVATURE"], np.sin(d["in_BANK"]))]
+    for seed in range(6):
+        n = int(np.random.default_rng(5000 + seed).integers(128, 1500))
+        cases.append(synthetic_closed_track(7000 + seed, n))
+    out = (C.c_longlong * 4)()
+    try:
+        L.hostsim_fwd_batch(1)
+        L.hostsim_fwd_batch_counters(out, 1)
+        for x, y, r, sb in cases:
+            o = O.qss(x, y, r, sb, ov, 0)
+            for impl in (102, 104, 108):
+                h = H.qss(impl, x[None], y[None], r[None], sb, hv)
+                assert h["status"][0] == 0
+                for k in ("v", "a", "lat", "time"):
+                    assert np.array_equal(h[k][0], o[k]), (impl, k)
+                assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
+        L.hostsim_fwd_batch_counters(out, 1)
+        assert out[1] > 0 and out[0] > 0        # members were committed in batches
+    finally:
+        L.hostsim_fwd_batch(0)
+
+
 @pytest.mark.parametrize("split", [2, 7, 16])
 def test_eval_sample_range_split(split):
     """Splitting a candidate's samples over lanes (eval_range) gives the same bits as one walk over all of them,
