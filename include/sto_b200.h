@@ -170,7 +170,7 @@ int sto_arc_sections_f64(const double* t, int nt, const double* cx, const double
 /* Batch of coefficient sets on SHARED knots (any degree 1..5): the optimiser-loop shape of the path - the reference's
  * TrajectoryOptimizer edits control points of one spline and calls sample_along(ts=...) + run_simulation after every
  * edit (optimization/optimizer.py:196-211,276-289).  t[nt], ts[N] shared; cx, cy [nt-k-1][ld] sample-major; outputs as
- * sto_sample_f64.  N <= 65535. */
+ * sto_sample_f64. */
 int sto_sample_splines_f64(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts, int N,
                            int B, int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
                            double* chord_norm, void* stream);

@@ -223,8 +223,8 @@ __global__ void eval_spline_kernel(sto::SplineEvalArgs A) {
 
 __global__ void eval_spline_batch_kernel(sto::SplineBatchArgs A) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (b < A.B) sto::eval_spline_batch_sample(A, j, b);
+    if (b >= A.B) return;
+    for (int j = blockIdx.y; j < A.N; j += gridDim.y) sto::eval_spline_batch_sample(A, j, b);
 }
 
 // Trajectory.fill_bounds (reference models/trajectory.py:83-141): nearest intersection of the two-sided segment
@@ -263,13 +263,14 @@ __global__ void arc_sections_kernel(sto::ArcArgs A) {
 __global__ void chord_kernel(const double* x, const double* y, int N, int B, int ld_in, double* dd, double* df,
                              int ld) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
     if (b >= B) return;
-    int n = (i + 1 == N) ? 0 : i + 1;
-    double x0 = x[sto::at(i, ld_in, b)], y0 = y[sto::at(i, ld_in, b)];
-    double x1 = x[sto::at(n, ld_in, b)], y1 = y[sto::at(n, ld_in, b)];
-    dd[sto::at(i, ld, b)] = sto::chord_qss(x0, y0, x1, y1);
-    df[sto::at(i, ld, b)] = sto::chord_norm(x0, y0, x1, y1);
+    for (int i = blockIdx.y; i < N; i += gridDim.y) {   // grid.y is capped at 65,535: longer tracks stride
+        int n = (i + 1 == N) ? 0 : i + 1;
+        double x0 = x[sto::at(i, ld_in, b)], y0 = y[sto::at(i, ld_in, b)];
+        double x1 = x[sto::at(n, ld_in, b)], y1 = y[sto::at(n, ld_in, b)];
+        dd[sto::at(i, ld, b)] = sto::chord_qss(x0, y0, x1, y1);
+        df[sto::at(i, ld, b)] = sto::chord_norm(x0, y0, x1, y1);
+    }
 }
 
 // The QSS kernels are latency bound (one dependent chain of FP64 divisions / square roots and scattered loads per
@@ -669,7 +670,7 @@ int sto_sample_spline_f64(const double* t, int nt, const double* cx, const doubl
 
 static int launch_spline_batch(const sto::SplineBatchArgs& A, cudaStream_t st) {
     const int block = (A.B >= 128) ? 128 : 32;
-    dim3 grid((A.B + block - 1) / block, A.N);
+    dim3 grid((A.B + block - 1) / block, A.N < 65535 ? A.N : 65535);
     eval_spline_batch_kernel<<<grid, block, 0, st>>>(A);
     STO_CUDA(cudaGetLastError());
     return STO_OK;
@@ -678,7 +679,7 @@ static int launch_spline_batch(const sto::SplineBatchArgs& A, cudaStream_t st) {
 int sto_sample_splines_f64(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts, int N,
                            int B, int ld, double* x, double* y, double* yaw, double* radius, double* chord_qss,
                            double* chord_norm, void* stream) {
-    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 1 || B < 1 || ld < B || N > 65535)
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 1 || B < 1 || ld < B)
         return fail(STO_ERR_INVALID, "bad spline batch sizes");
     if (!t || !cx || !cy || !ts) return fail(STO_ERR_INVALID, "t, cx, cy, ts must be non-NULL");
     sto::SplineBatchArgs A{t, nt, k, cx, cy, ts, N, B, ld, x, y, yaw, radius, chord_qss, chord_norm};
@@ -725,17 +726,17 @@ int sto_qss_f64(const double* x, const double* y, const double* radius, const do
         return fail(STO_ERR_INVALID, "ITERATION_FLAG (owner) is only tracked by STO_QSS_PLAIN");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t wld = ldof(B);
+    // the kernels work on one leading dimension (the workspace's); checked before anything is enqueued
+    if ((size_t)ld != wld) return fail(STO_ERR_INVALID, "sto_qss_f64 needs ld == round_up(B, 32)");
     Carver c(work);
     QssWork w = carve_qss(c, N, wld, impl, true, true);
     if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "qss workspace too small");
     {
-        dim3 g((B + 127) / 128, N);
+        dim3 g((B + 127) / 128, N < 65535 ? N : 65535);
         chord_kernel<<<g, 128, 0, st>>>(x, y, N, B, ld, w.dd, w.df, (int)wld);
         STO_CUDA(cudaGetLastError());
     }
-    // the kernel works on one leading dimension; radius comes in the caller's, so stage it if they differ
     const double* Rw = radius;
-    if ((size_t)ld != wld) return fail(STO_ERR_INVALID, "sto_qss_f64 needs ld == round_up(B, 32)");
     sto::QssArgs A{};
     A.dd = w.dd; A.df = w.df; A.R = Rw; A.sinb = sin_bank; A.N = N; A.B = B; A.ld = (int)wld; A.cap = w.cap;
     A.v = (out && out->speed) ? out->speed : w.v;      // memo kernel: outputs only (NULL = not materialised)
@@ -833,7 +834,7 @@ size_t sto_lap_splines_workspace_bytes(int N, int B, int impl) {
 int sto_lap_time_splines_f64(const double* t, int nt, int k, const double* cx, const double* cy, const double* ts,
                              const double* sin_bank, int N, int B, int ld, const sto_vehicle_f64* vehicle, int impl,
                              double* lap, int32_t* status, void* work, size_t work_bytes, void* stream) {
-    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 2 || N > 65535 || B < 1)
+    if (k < 1 || k > 5 || nt < 2 * (k + 1) || N < 2 || B < 1)
         return fail(STO_ERR_INVALID, "bad spline batch sizes");
     if (!t || !cx || !cy || !ts || !lap || !status || !work) return fail(STO_ERR_INVALID, "NULL argument");
     if (impl != STO_QSS_PLAIN && impl != STO_QSS_MEMO) return fail(STO_ERR_INVALID, "unknown impl");

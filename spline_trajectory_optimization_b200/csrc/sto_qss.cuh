@@ -46,9 +46,11 @@ struct QssArgs {
 
 // One front step (simulator.py:159-199 backward, :262-301 forward): the greedy speed g at the next sample
 // reachable from state (vp, ap) over chord dd, and whether it is feasible (min_state <= g).
+// `respawn` = the reference's test at simulator.py:239 (`g > max_curve_speed or g < min_state_speed`), read only when
+// the step is infeasible: false for NaN operands, in which case the front just stops.
 template <bool FWD>
 STO_HD bool front_step(const sto_vehicle_f64& V, double vp, double ap, double dd, double Rq, double gsbq,
-                       double& g, double& vp2) {
+                       double& g, double& vp2, bool& respawn) {
     double dt = dd / vp;
     double md = dt * V.max_jerk;
     double hi = ap + md, lo = ap - md;
@@ -67,6 +69,7 @@ STO_HD bool front_step(const sto_vehicle_f64& V, double vp, double ap, double dd
     }
     double mc = calc_v(max_lat_acc(V, ap), Rq, gsbq);
     g = py_min3(smax, mc, V.max_speed);
+    respawn = (g > mc) || (g < smin);
     return smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
 }
 
@@ -87,7 +90,8 @@ STO_HD bool row_step(const QssArgs& A, const sto_vehicle_f64& V, int b, int p, i
         return true;
     }
     double g, vp2;
-    const bool valid = front_step<FWD>(V, vp, ap, dd, Rq, gq, g, vp2);
+    bool respawn;
+    const bool valid = front_step<FWD>(V, vp, ap, dd, Rq, gq, g, vp2, respawn);
     if (valid) {
         const double vq = A.v[at(q, ld, b)];
         if (vq < g) return true;  // a slower speed is already stored: stop (:211-216 / :313-318)
@@ -96,7 +100,7 @@ STO_HD bool row_step(const QssArgs& A, const sto_vehicle_f64& V, int b, int p, i
         if (OWNER) A.owner[at(q, ld, b)] = turn;
         return false;
     }
-    if (!FWD) {  // infeasible backward step: re-initialise q as a fresh turn and spawn a row (:238-254)
+    if (!FWD && respawn) {  // infeasible backward step: re-initialise q as a fresh turn and spawn a row (:238-254)
         A.v[at(q, ld, b)] = init_speed(lat0, Rq, gq, V.max_speed);
         A.a[at(q, ld, b)] = 0.0;
         if (OWNER) A.owner[at(q, ld, b)] = q;

@@ -218,7 +218,7 @@ STO_HD void memo_invalidate_cont(const MemoCtx& C, int p, int q, int d, int N) {
 // front_step<FWD> of sto_qss.cuh with the direction as a run-time value (lanes of one warp may be in different
 // sub-passes): the same operations on the same operands, selected instead of branched, so results are bit-identical.
 STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double dd, double Rq,
-                          double gsbq, double& g, double& vp2) {
+                          double gsbq, double& g, double& vp2, bool& respawn) {
     double dt = dd / vp;
     double md = dt * V.max_jerk;
     double hi = ap + md, lo = ap - md;
@@ -233,6 +233,7 @@ STO_HD bool front_step_rt(const sto_vehicle_f64& V, bool fwd, double vp, double 
     const double smax = fwd ? s_hi : s_lo, smin = fwd ? s_lo : s_hi;
     double mc = calc_v(max_lat_acc(V, ap), Rq, gsbq);
     g = py_min3(smax, mc, V.max_speed);
+    respawn = (g > mc) || (g < smin);   // simulator.py:239, read only when the step is infeasible (false for NaN operands)
     return smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
 }
 
@@ -258,7 +259,8 @@ STO_HD EvalRes eval_core(const sto_vehicle_f64& V, bool fwd, double vp, double a
     // (no early exit before the arithmetic: a branch here makes the compiler split the record fetch into two
     //  dependent round trips; with vp == 0 the step below just produces inf/nan that is never stored)
     double g, vp2;
-    const bool valid = front_step_rt(V, fwd, vp, ap, dd, Rq, gq, g, vp2);
+    bool respawn;
+    const bool valid = front_step_rt(V, fwd, vp, ap, dd, Rq, gq, g, vp2, respawn);
     EvalRes r;
     r.v_new = 0.0; r.a_new = 0.0;
     if (vp == 0.0) { r.kind = EV_ZERO; return r; }
@@ -270,7 +272,9 @@ STO_HD EvalRes eval_core(const sto_vehicle_f64& V, bool fwd, double vp, double a
         r.kind = (!same_bits(vq, g) || !same_bits(aq_old, aq)) ? EV_WRITE : EV_KEEP;
         return r;
     }
-    if (fwd) { r.kind = EV_STOP; return r; }
+    // infeasible: the front stops; a backward front re-initialises q and spawns a row only under the reference's test
+    // (simulator.py:239), otherwise - NaN operands - nothing is touched, which is what the STOP memo records
+    if (fwd || !respawn) { r.kind = EV_STOP; return r; }
     const double vi = init_speed(lat0, Rq, gq, V.max_speed);
     r.v_new = vi;
     r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;

@@ -87,3 +87,22 @@ def synthetic_closed_track(seed, n):
         R = np.where(np.abs(kappa) > 1e-9, 1.0 / np.abs(kappa), np.inf)
     bank = rng.uniform(-0.05, 0.1, n) * (rng.random() < 0.5)
     return x, y, R, np.sin(bank)
+
+
+def nan_cases():
+    """NaN-producing inputs inside a live line (reference simulator.py:239: the spawn test `g > max_curve_speed or
+    g < min_state_speed` is false for NaN, so an infeasible step on NaN operands only stops the front)."""
+    x, y, r, sb = synthetic_closed_track(3, 300)
+    cases = {}
+    xr, yr, rr = x.copy(), y.copy(), r.copy()
+    rr[120] = np.nan
+    cases["nan_radius"] = (xr, yr, rr, sb)
+    xp, yp, rp = x.copy(), y.copy(), r.copy()
+    xp[57] = np.nan
+    cases["nan_position"] = (xp, yp, rp, sb)
+    cases["all_nan"] = (np.full_like(x, np.nan), np.full_like(y, np.nan), np.full_like(r, np.nan), sb)
+    xm, ym, rm = x.copy(), y.copy(), r.copy()
+    rm[10:14] = np.nan
+    ym[200] = np.nan
+    cases["nan_mixed"] = (xm, ym, rm, sb)
+    return cases

@@ -580,6 +580,65 @@ def test_status_flags_and_chunked_host_path(sto):
     assert np.array_equal(lap_one[:8], lap_one[88:])
 
 
+@pytest.mark.parametrize("case", ["nan_radius", "nan_position", "all_nan", "nan_mixed"])
+def test_qss_nan_inputs_equal_oracle(sto, case):
+    """NaN inside a live line: the reference's spawn test (simulator.py:239, `g > max_curve_speed or g < min_state_speed`)
+    is false for NaN, so such a front only stops.  Both kernels must EQUAL the oracle - status, front-step count, outer
+    iterations, speeds and accelerations (NaN pattern included) - with the healthy neighbours in the batch untouched."""
+    from helpers import nan_cases
+    from spline_trajectory_optimization_b200 import _lib
+    d = golden("sim_s10k3_i2")
+    veh, ov = _lib.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    x, y, r, sb = nan_cases()[case]
+    from helpers import synthetic_closed_track
+    xh, yh, rh, _ = synthetic_closed_track(3, 300)             # the same line without the NaN, as lanes 0 and 2
+    X, Y, R = np.stack([xh, x, xh]), np.stack([yh, y, yh]), np.stack([rh, r, rh])
+    o, oh = O.qss(x, y, r, sb, ov, 0), O.qss(xh, yh, rh, sb, ov, 0)
+    assert o["status"] == 2 and oh["status"] == 0
+    for impl in ("plain", "memo"):
+        res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=3, sin_bank=sb, impl=sto.IMPL[impl])
+        torch.cuda.synchronize()
+        st = res["status"][:3].cpu().numpy()
+        assert list(st) == [0, _lib.CAND_NAN, 0], (impl, st)
+        assert float(res["summary"][6, 1]) == o["steps"] and float(res["summary"][7, 1]) == o["iters"] + 1, impl
+        assert np.array_equal(res["speed"][:, 1].cpu().numpy(), o["v"], equal_nan=True), impl
+        assert np.array_equal(res["lon_acc"][:, 1].cpu().numpy(), o["a"], equal_nan=True), impl
+        assert np.isnan(float(res["lap"][1]))
+        for c in (0, 2):
+            assert np.array_equal(res["speed"][:, c].cpu().numpy(), oh["v"]) and float(res["lap"][c]) == oh["lap"]
+            assert float(res["summary"][6, c]) == oh["steps"]
+
+
+def test_fused_path_nan_offset_terminates(sto):
+    """One NaN offset makes every coefficient of that line NaN (the fit is periodic): the fit flags it, the QSS must not
+    spin on it (round 1 re-spawned every row until the 64 N iteration cap: minutes for one line at N = 2895) and the
+    other lines of the batch keep their bits.  Status = DEGENERATE_FIT | NAN, lap NaN, the oracle agrees."""
+    import time
+    from spline_trajectory_optimization_b200 import _lib
+    d = golden("cand_m2895_n2895")
+    ov = O.make_vehicle(*veh_args(d))
+    nrm = np.stack([-np.sin(d["centre_yaw"]), np.cos(d["centre_yaw"])], axis=1)
+    off = d["offsets"].copy()
+    B = off.shape[0]
+    off[1, 1000] = np.nan
+    olap, ost = O.lap_batch(d["centre_x"], d["centre_y"], nrm[:, 0], nrm[:, 1], off, d["ts"], np.zeros(len(d["ts"])),
+                            ov, n_threads=2, ref_pow=0)
+    assert ost[1] != 0 and np.isnan(olap[1])
+    for impl in ("memo", "plain"):
+        ev = _evaluator(sto, d, impl=impl)
+        ev.lap_times(to_sm(d["offsets"]), B=B)                 # warm-up (module load, workspace)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lap, st = ev.lap_times(to_sm(off), B=B)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        lap, st = lap.cpu().numpy(), st.cpu().numpy()
+        assert st[1] == (_lib.CAND_DEGENERATE_FIT | _lib.CAND_NAN) and np.isnan(lap[1]), (impl, st)
+        keep = np.arange(B) != 1
+        assert not st[keep].any() and np.array_equal(lap[keep], olap[keep]), impl
+        assert dt < (5.0 if impl == "memo" else 20.0), (impl, dt)
+
+
 def test_control_point_variants_batched(sto):
     """§8 f-2 (optimiser-loop batching): the reference's edit -> wrap -> sample_along(ts) -> run_simulation sequence for
     six control-point variants of the s=30,k=5 Monza line, scored in one launch."""

@@ -344,3 +344,23 @@ def test_fit_fitpack_small_and_random_lines():
             assert np.array_equal(hcx[0], rx) and np.array_equal(hcy[0], ry), (M, rep)
             ot, ocx, ocy = O.fit_periodic_cubic(pts)
             assert np.array_equal(ot, t) and np.array_equal(ocx, rx) and np.array_equal(ocy, ry), (M, rep)
+
+
+@pytest.mark.parametrize("case", ["nan_radius", "nan_position", "all_nan", "nan_mixed"])
+def test_qss_nan_inputs_equal_oracle(case):
+    """Both schedule kernels (host build) on NaN inputs: same status, same step / iteration counts and the same
+    speed / acceleration arrays (NaN pattern included) as the oracle - not just 'status != 0'."""
+    d = golden("sim_s10k3_i2")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    from helpers import nan_cases
+    x, y, r, sb = nan_cases()[case]
+    o = O.qss(x, y, r, sb, ov, 0)
+    assert o["status"] == 2                                   # STO_ORACLE_NAN
+    assert o["iters"] < 4 * len(x)                            # terminates like a healthy line, far below the 64 N cap
+    for impl in (0, 1, 104, 108):
+        h = H.qss(impl, x[None], y[None], r[None], sb, hv)
+        assert h["status"][0] == 2, (impl, h["status"][0])    # STO_CAND_NAN, nothing else
+        assert h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1, impl
+        for k in ("v", "a"):
+            assert np.array_equal(h[k][0], o[k], equal_nan=True), (impl, k)
+        assert np.isnan(h["lap"][0]) and np.isnan(o["lap"])
