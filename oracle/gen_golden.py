@@ -268,6 +268,42 @@ def task_control_points():
     _save("ctrl_s30k5_n578", **d)
 
 
+def task_ttl():
+    """TTL wire format and table I/O of the unmodified reference (models/trajectory.py:143-156 fill_distance, :202-209
+    Trajectory.save/load, :312-358 save_ttl/load_ttl): a 48-row slice of the simulated s=30,k=5 line written with and
+    without an origin; the file TEXT is the golden (REGION as int, repr of every float64)."""
+    import tempfile
+    rh.install()
+    from spline_traj_optm.models.trajectory import BSplineTrajectory, Trajectory, load_ttl, save_ttl
+    spl = BSplineTrajectory(rh.load_xy(rh.monza_csv("center")), 30.0, 5)
+    full = spl.sample_along(120.0)
+    out, _, _ = rh.simulate(full)
+    n = len(out)
+    traj = Trajectory(n, ttl_num=7, origin=(45.6189, 9.2811, 183.25))
+    traj.points = np.array(out)
+    traj.points[:, 8] = (np.arange(n) * 3) % 5                    # REGION codes
+    traj.points[:, 2] = 0.25 * np.arange(n)                       # Z
+    traj.points[:, 9:13] = traj.points[:, [0, 1, 0, 1]] + np.array([1.5, -2.5, -3.25, 4.125])   # bounds
+    d = dict(points=np.array(traj.points), ttl_num=np.int64(7), origin=np.array(traj.origin))
+    with tempfile.TemporaryDirectory() as tmp:
+        f1, f2, f3 = (os.path.join(tmp, x) for x in ("a.csv", "b.csv", "c.csv"))
+        save_ttl(f1, traj)
+        d["ttl_text_origin"] = np.array(open(f1).read())
+        back = load_ttl(f1)
+        d["ttl_loaded_points"] = np.array(back.points)
+        d["ttl_loaded_meta"] = np.array([back.ttl_num, *back.origin], dtype=np.float64)
+        traj.origin = None
+        save_ttl(f2, traj)
+        d["ttl_text_noorigin"] = np.array(open(f2).read())
+        Trajectory.save(f3, traj)
+        d["table_text"] = np.array(open(f3).read())
+        d["table_loaded_points"] = np.array(Trajectory.load(f3).points)
+    fd = traj.copy()
+    fd.fill_distance()
+    d["fill_distance_bwd"], d["fill_distance_fwd"] = np.array(fd.points[:, 6]), np.array(fd.points[:, 7])
+    _save("ttl_s30k5_n48", **d)
+
+
 TASKS = [
     (task_raw, ()),
     (task_track_splines, ()),
@@ -283,6 +319,7 @@ TASKS = [
     (task_table_vehicle, ()),
     (task_synthetic_tables, ()),
     (task_control_points, ()),
+    (task_ttl, ()),
     (task_candidates, (10.0, 8, 1, "cand_m579_n579")),
     (task_candidates, (10.0, 3, 2, "cand_m579_n1158")),
     (task_candidates, (2.0, 3, 1, "cand_m2895_n2895")),

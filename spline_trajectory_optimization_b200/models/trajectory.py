@@ -65,7 +65,7 @@ def _ray_ring_hits(points, normals, ring, max_dist):
         j = np.argmin(tt, axis=1)
         rows = np.arange(tt.shape[0])
         has = np.isfinite(tt[rows, j])
-        tsel = t[rows, j]
+        tsel = np.where(has, t[rows, j], 0.0)
         hp = points[lo:lo + step] + tsel[:, None] * normals[lo:lo + step]
         hit[lo:lo + step][has] = hp[has]
         found[lo:lo + step] = has

@@ -677,6 +677,26 @@ def test_fill_bounds_on_device(sto):
     assert far[0, Trajectory.LEFT_BOUND_X] == 1e5 and far[0, Trajectory.RIGHT_BOUND_Y] == 1e5
 
 
+@pytest.mark.parametrize("closed", [False, True])
+def test_fill_bounds_reference_semantics_on_device(sto, closed):
+    """The hand-derived fill_bounds cases of tests/test_track_io.py (reference models/trajectory.py:83-141: two-sided
+    200 m segment, nearest Point wins whichever side it is on, no hit -> the point itself, ring with / without the
+    repeated closing vertex) through sto_fill_bounds_f64, and device == NumPy path bit for bit."""
+    from test_track_io import _closed, fill_bounds_cases
+    from spline_trajectory_optimization_b200.models.trajectory import Trajectory
+    for P, yaw, lring, rring, eleft, eright, fl, fr in fill_bounds_cases():
+        lr, rr = (_closed(lring), _closed(rring)) if closed else (lring, rring)
+        out = {}
+        for device in (True, False):
+            t = Trajectory(1)
+            t.points[0, [Trajectory.X, Trajectory.Y]] = P
+            t.points[0, Trajectory.YAW] = yaw
+            t.fill_bounds(lr, rr, max_dist=100.0, device=device)
+            out[device] = t.points[0, 9:13].copy()
+        assert np.array_equal(out[True], out[False]), (P, out)
+        assert np.allclose(out[True][:2], eleft, atol=1e-12) and np.allclose(out[True][2:], eright, atol=1e-12), (P, out)
+
+
 def test_fast_fp64_division_and_sqrt_selftest(sto):
     """The FITPACK solver's rotation chain runs its divisions and square roots as flagged, branch-free copies of nvcc's
     fast paths (csrc/sto_common.cuh).  On 3 x 2^27 operations over every kind of operand: not one result differs from the
