@@ -87,7 +87,13 @@ typedef struct sto_profile_out_f64 {
 int sto_abi_version(void);
 const char* sto_last_error(void);     /* thread-local text of the last failure */
 int sto_device_count(void);           /* number of sm_100-class devices visible */
-int sto_release(void);                /* frees the device arena cached by the *_host entry points */
+int sto_release(void);                /* frees the per-device arenas / streams cached by the *_host entry points */
+/* Developer tuning overrides, 0 = automatic: "fit_split" (lanes per candidate of the fit kernels), "qss_lanes" (candidates
+ * per warp), "qss_group" (lanes per candidate of the memoised QSS kernel) - powers of two <= 32 - and "qss_planes" (1 bit
+ * planes in shared memory, 2 global, 3 all global, 4 CONT planes shared + rest global).  The same values are read ONCE
+ * from the environment (STO_FIT_SPLIT, STO_QSS_LANES, STO_QSS_GROUP, STO_QSS_PLANES, STO_FIT_SOLVER) when the library is
+ * loaded; nothing consults the environment afterwards.  Results never depend on these, only speed. */
+int sto_set_tuning(const char* key, int value);
 
 /* ---- periodic cubic fit: BSplineTrajectory(points, s=0.0, k=3), models/trajectory.py:213-223 ------ */
 /*
@@ -112,7 +118,7 @@ size_t sto_fit_workspace_bytes(int M, int B);
  * The reference's QSS is a discontinuous function of its inputs: with the two approximate solvers 1-2 lines in 500
  * land on the other side of a stop / overwrite decision and their laps move by 1e-6 .. 1e-4 s. */
 enum { STO_FIT_THOMAS = 0, STO_FIT_BLOCKS = 1, STO_FIT_FITPACK = 2 };
-int sto_set_fit_solver(int solver);          /* process-wide; returns STO_ERR_INVALID for an unknown value */
+int sto_set_fit_solver(int solver);          /* process-wide (atomic); returns STO_ERR_INVALID for an unknown value */
 int sto_get_fit_solver(void);
 int sto_fit_solver_lanes(int M, int B);      /* lanes per candidate the selected solver's kernel uses for this size */
 int sto_fit_periodic_cubic_f64(const double* centre_x, const double* centre_y, const double* normal_x,
@@ -217,7 +223,8 @@ int sto_last_stage_ms(float* ms4);
  * Same with HOST buffers (the call a ctypes binding makes): offsets_host[B][M] CANDIDATE-major as a user
  * holds them (row b = one line), track arrays [M], ts[N], lap_host[B], status_host[B].  Copies inputs to the
  * device, transposes on the device, runs the fused path in chunks that fit `max_work_bytes` (0 = choose),
- * copies laps back and synchronises.  `device` selects the GPU.
+ * copies laps back and synchronises.  `device` selects the GPU.  Thread-safe: each device has its own arena, stream
+ * and mutex, so threads driving different GPUs run concurrently and callers of one GPU are serialised.
  */
 int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const double* normal_x,
                           const double* normal_y, const double* sin_bank, const double* ts,
@@ -230,6 +237,14 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
  * best_lap[0], best_idx[0] (device).  Ties resolve to the lowest index. */
 int sto_argmin_f64(const double* lap, const int32_t* status, int B, double* best_lap, int64_t* best_idx,
                    void* stream);
+
+/* Candidate-sharded batches (one process per GPU): a rank's winner as ONE 16-byte pair {best lap, GLOBAL candidate index as
+ * a double (-1 if the shard has no valid candidate; indices < 2^53 are exact)} = argmin over its shard with `index_base`
+ * added, ready for a single all-gather of 16 bytes per rank; then the argmin over the n gathered pairs (lowest global index
+ * wins ties, NaN / -1 pairs ignored).  `scratch` = 16 bytes of device memory.  All pointers DEVICE. */
+int sto_argmin_pair_f64(const double* lap, const int32_t* status, int B, int64_t index_base, double* pair,
+                        void* scratch, void* stream);
+int sto_argmin_pairs_f64(const double* pairs, int n, double* best_lap, int64_t* best_idx, void* stream);
 
 /* Self-test of the branch-free IEEE division / square root used by the FITPACK solver's rotation chain
  * (csrc/sto_common.cuh): 2^27 operations on operands of every kind (all bit patterns, mid-range magnitudes of both signs,

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "sto_last_error": (C.c_char_p, []),
     "sto_device_count": (C.c_int, []),
     "sto_release": (C.c_int, []),
+    "sto_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "sto_fit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "sto_fit_periodic_cubic_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [_vp] * 4 + [_vp, C.c_size_t, _vp]),
     "sto_sample_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int] + [_vp] * 6 + [_vp]),
@@ -67,6 +68,8 @@ _SIGNATURES = {
     "sto_selftest_fp64": (C.c_int, [C.c_ulonglong] + [C.POINTER(C.c_longlong)] * 3),
     "sto_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
     "sto_argmin_f64": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "sto_argmin_pair_f64": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, _vp, _vp, _vp]),
+    "sto_argmin_pairs_f64": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "sto_transpose_f64": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -29,6 +29,37 @@ def smooth_offsets(M, B, dist_left, dist_right, seed=1234, harmonics=8, amplitud
     return off
 
 
+def smooth_offsets_device(M, lo, hi, dist_left, dist_right, device, seed=1234, harmonics=8, amplitude=1.5, margin=1.0):
+    """Candidates lo .. hi-1 of a (conceptually unbounded) batch, generated ON THE DEVICE and returned sample-major
+    [M, round_up(hi - lo, 32)] (the layout the kernels read): the same family of lines as `smooth_offsets` - 8 sine
+    harmonics, amplitudes ~ N(0, 1.5 / h) m, clipped to the bounds minus the margin, candidate 0 = the centre line -
+    with torch's generator instead of NumPy's (different random lines; the big configurations only need them
+    synthetic).  A candidate's offsets depend on (seed, its global index) only, never on how the batch is sharded."""
+    import torch
+    n = hi - lo
+    ld = (n + 31) & ~31
+    out = torch.zeros((M, ld), dtype=torch.float64, device=device)
+    ang = (2.0 * np.pi / M) * torch.arange(M, dtype=torch.float64, device=device)
+    lo_b = -torch.clamp(torch.as_tensor(np.asarray(dist_right, dtype=np.float64), device=device) - margin, min=0.0)
+    hi_b = torch.clamp(torch.as_tensor(np.asarray(dist_left, dtype=np.float64), device=device) - margin, min=0.0)
+    scale = amplitude / torch.arange(1, harmonics + 1, dtype=torch.float64, device=device)
+    chunk = 4096
+    for c in range(lo // chunk, (hi + chunk - 1) // chunk):
+        g = torch.Generator(device=device)
+        g.manual_seed(int(seed) * 1000003 + c)
+        amp = torch.randn((chunk, harmonics), generator=g, dtype=torch.float64, device=device) * scale
+        phi = torch.rand((chunk, harmonics), generator=g, dtype=torch.float64, device=device) * (2.0 * np.pi)
+        b0, b1 = max(lo, c * chunk), min(hi, (c + 1) * chunk)
+        rows = slice(b0 - c * chunk, b1 - c * chunk)
+        acc = torch.zeros((M, b1 - b0), dtype=torch.float64, device=device)
+        for h in range(1, harmonics + 1):
+            acc += amp[rows, h - 1][None, :] * torch.sin(h * ang[:, None] + phi[rows, h - 1][None, :])
+        out[:, b0 - lo:b1 - lo] = torch.minimum(torch.maximum(acc, lo_b[:, None]), hi_b[:, None])
+    if lo == 0:
+        out[:, 0] = 0.0
+    return out
+
+
 def banked_oval(straight=800.0, radius=250.0, width=15.0, bank_deg=9.0, blend=100.0, spacing=8.0):
     """Synthetic banked oval (BASELINE config 4): 4-column ``x, y, z, bank`` centre line plus left/right bounds.
     Two straights + two semicircles, counter-clockwise; bank ramps 0 -> bank_deg over ``blend`` metres into each

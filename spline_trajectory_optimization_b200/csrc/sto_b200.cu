@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC ...
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,29 @@ int fail_cuda(cudaError_t e, const char* where) {
         if (e_ != cudaSuccess) return fail_cuda(e_, #call);   \
     } while (0)
 
+// Developer tuning overrides (0 = automatic).  Read from the STO_* environment variables ONCE, when the library is
+// loaded, and settable afterwards through sto_set_tuning(); the launch paths only read these atomics.
+struct Tuning {
+    std::atomic<int> fit_split{0};    // lanes per candidate of the fit kernels (power of two <= 32)
+    std::atomic<int> qss_lanes{0};    // candidates per warp of the QSS kernels (power of two <= 32)
+    std::atomic<int> qss_group{0};    // lanes per candidate of the memoised QSS kernel (1, 2, 4, 8, 16, 32)
+    std::atomic<int> qss_planes{0};   // 1 = bit planes in shared memory, 2 = global (mixed decided by residency),
+                                      // 3 = all global, 4 = CONT planes shared + live / STOP planes global
+    std::atomic<int> fit_solver{STO_FIT_FITPACK};   // sto_set_fit_solver
+};
+Tuning g_tune;
+inline bool pow2_le32(int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; }
+struct TuningFromEnv {
+    TuningFromEnv() {
+        if (const char* e = getenv("STO_FIT_SPLIT")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.fit_split = v; }
+        if (const char* e = getenv("STO_FIT_SOLVER")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.fit_solver = v; }
+        if (const char* e = getenv("STO_QSS_LANES")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_lanes = v; }
+        if (const char* e = getenv("STO_QSS_GROUP")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_group = v; }
+        if (const char* e = getenv("STO_QSS_PLANES"))
+            g_tune.qss_planes = (e[0] == 's') ? 1 : (e[0] != 'g') ? 0 : (e[1] == '\0') ? 2 : (e[1] == '0') ? 3 : 4;
+    }
+} g_tuning_from_env;
+
 // 32-thread CTAs until every SM has a few warps: the QSS is latency-bound, so spreading warps over all 148
 // SMs matters more than CTA size; larger batches use fuller CTAs to cut launch/scheduling overhead.
 int pick_block(int B) {
@@ -45,10 +69,7 @@ int pick_block(int B) {
 inline int grid_for(int B, int block) { return (B + block - 1) / block; }
 // Lanes per candidate for the fit: 4 (three recurrences + split row work) while the batch leaves SMs idle.
 int pick_fit_split(int B) {
-    if (const char* e = getenv("STO_FIT_SPLIT")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
-    }
+    if (const int v = g_tune.fit_split.load()) return v;
     // measured on B200 (Monza, M = 2895): 4,096 candidates 10.2 / 7.6 / 5.5 / 4.5 / 4.4 ms at 1 / 2 / 4 / 8 / 16 lanes;
     // 32,768 candidates 12.1 / 9.5 / 12.8 / 20.0 ms at 1 / 2 / 4 / 8 lanes
     if ((long long)B * 8 <= 148LL * 8 * 32) return 8;
@@ -68,31 +89,20 @@ int pick_fit_split(int B) {
 //   B =  4096: Thomas x8 4.2 | 34.3   blocks x8  1.81 | 16.1
 //   B = 16384: Thomas x1 8.8 | 71.2   blocks x4  3.60 | 29.8
 //   B = 32768: Thomas x2 8.7          blocks x2  5.9          B = 65536: Thomas x1 11.4, blocks x1 9.2
-int g_fit_solver = STO_FIT_FITPACK;
 struct FitPlan { int split; int solver; };
 FitPlan pick_fit_plan(int M, int B) {
-    int solver = g_fit_solver;
-    if (const char* e = getenv("STO_FIT_SOLVER")) {
-        const int v = atoi(e);
-        if (v >= 0 && v <= 2) solver = v;
-    }
+    const int solver = g_tune.fit_solver.load();
     if (solver == STO_FIT_THOMAS) return FitPlan{pick_fit_split(B), solver};
     if (solver == STO_FIT_FITPACK) {
         // the rotation chain runs on one lane (two for the periodic rows); the other lanes of a group only speed up the
         // row phases (segments, running sum, fpbspl values).  Measured (M = 2895): B = 64: 5.1 / 5.4 / 5.7 ms at
         // 32 / 16 / 8 lanes; B = 4,096: 7.1 ms at 8 lanes, 12.7 at 16
         int lanes = (B <= 256) ? 32 : (B <= 1024) ? 16 : pick_fit_split(B);
-        if (const char* e = getenv("STO_FIT_SPLIT")) {
-            const int v = atoi(e);
-            if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
-        }
+        if (const int v = g_tune.fit_split.load()) lanes = v;
         return FitPlan{lanes, solver};
     }
     int lanes = (B <= 512) ? 32 : (B <= 2048) ? 16 : (B <= 8192) ? 8 : (B <= 24576) ? 4 : (B <= 49152) ? 2 : 1;
-    if (const char* e = getenv("STO_FIT_SPLIT")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
-    }
+    if (const int v = g_tune.fit_split.load()) lanes = v;
     if (M < 256) lanes = 1;   // one block (sto::fit_part_blocks): nothing to share
     return FitPlan{lanes, STO_FIT_BLOCKS};
 }
@@ -414,6 +424,30 @@ __global__ void argmin_kernel(const double* lap, const int32_t* status, int B, d
     }
 }
 
+// Multi-GPU reduction helpers (sharding.py): a rank's (best lap, GLOBAL candidate index) as one 16-byte pair, ready for a
+// single all-gather, and the argmin over the gathered pairs (lowest global index wins ties, NaN / -1 pairs ignored).
+__global__ void argmin_pair_kernel(const double* best_lap, const long long* best_idx, long long index_base, double* pair) {
+    const long long i = best_idx[0];
+    pair[0] = (i >= 0) ? best_lap[0] : nan("");
+    pair[1] = (i >= 0) ? (double)(i + index_base) : -1.0;   // indices < 2^53 are exact in a double
+}
+__global__ void argmin_pairs_kernel(const double* pairs, int n, double* best_lap, long long* best_idx) {
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int r = threadIdx.x; r < n; r += 32) {
+        const double v = pairs[2 * r];
+        const long long i = (long long)pairs[2 * r + 1];
+        if (!(v == v) || i < 0) continue;
+        if (bi < 0 || v < bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) { *best_lap = (bi >= 0) ? bv : nan(""); *best_idx = bi; }
+}
+
 // Optional stage timing of the fused path (bench.py's roofline leg): CUDA events recorded on the launching
 // stream between the stages; nothing synchronises until sto_last_stage_ms() is called.
 struct StageTimer {
@@ -464,12 +498,8 @@ __global__ void qss_memo_mixed_kernel(sto::QssArgs A, sto::MemoWork W, int lanes
 // Candidates per warp for the QSS kernels: aim for a few warps on each of the 148 SMs before filling warps.
 int pick_lanes(int B, size_t smem_per_candidate) {
     int lanes = 32;
-    if (const char* e = getenv("STO_QSS_LANES")) {
-        int v = atoi(e);
-        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lanes = v;
-    } else {
-        while (lanes > 4 && (B + lanes - 1) / lanes < 148 * 2) lanes >>= 1;
-    }
+    if (const int v = g_tune.qss_lanes.load()) lanes = v;
+    else while (lanes > 4 && (B + lanes - 1) / lanes < 148 * 2) lanes >>= 1;
     while (lanes > 1 && smem_per_candidate * lanes > kMemoSmemBudget) lanes >>= 1;
     return lanes;
 }
@@ -489,8 +519,8 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         // bound by the per-candidate dependent chain, and LDS beats an L1 hit), global memory (L1/L2 cached) beyond
         // that, where throughput is bound by how many candidates an SM can keep in flight (measured on B200, Monza:
         // 4,096 candidates 86 ms smem vs 92 ms global; 32,768 candidates 299 ms smem vs 186 ms global).
-        const char* pl = getenv("STO_QSS_PLANES");   // tuning override: "s" / "g"
-        const bool global_planes = pl ? (pl[0] == 'g')
+        const int pl = g_tune.qss_planes.load();   // tuning override (see Tuning)
+        const bool global_planes = pl ? (pl >= 2)
                                       : ((size_t)A.B * sto::memo_plane_bytes(A.N) > (size_t)148 * kMemoSmemBudget);
         if (global_planes) {
             const int lanes = pick_lanes(A.B, 0);
@@ -499,7 +529,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
             // mixed placement while every warp of the batch stays resident with its CONT planes in shared memory
             // (measured: 32,768 candidates 168 ms mixed vs 184 ms all-global; 131,072 candidates 662 vs 559 ms)
             const int resident = 148 * (int)((size_t)227 * 1024 / (mixed_smem + 1024));
-            const bool mixed = (pl && pl[0] == 'g' && pl[1] != '\0') ? (pl[1] != '0') : (warps <= resident);
+            const bool mixed = (pl >= 3) ? (pl == 4) : (warps <= resident);
             if (mixed && mixed_smem <= kMemoSmemBudget / 4) {
                 STO_CUDA(cudaFuncSetAttribute(qss_memo_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)mixed_smem));
@@ -515,10 +545,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         // measured on B200 (Monza, 4,096 candidates): 4 candidates x 8 lanes per warp 63.3 ms, 8 x 4 lanes 65.1 ms,
         // 8 x 2 lanes 72.9 ms; larger batches fill the SMs with 8 candidates per warp
         int G = ((A.B + 3) / 4 <= 148 * 8) ? 8 : 4;
-        if (const char* e = getenv("STO_QSS_GROUP")) {
-            const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) G = v;
-        }
+        if (const int v = g_tune.qss_group.load()) G = v;
         const size_t per_cand = sto::memo_plane_bytes(A.N);
         int cpw = pick_lanes(A.B, per_cand);
         if (cpw > 32 / G) cpw = 32 / G;
@@ -553,10 +580,20 @@ const char* sto_last_error(void) { return g_err.c_str(); }
 int sto_set_fit_solver(int solver) {
     if (solver != STO_FIT_THOMAS && solver != STO_FIT_BLOCKS && solver != STO_FIT_FITPACK)
         return fail(STO_ERR_INVALID, "unknown fit solver");
-    g_fit_solver = solver;
+    g_tune.fit_solver.store(solver);
     return STO_OK;
 }
-int sto_get_fit_solver(void) { return g_fit_solver; }
+int sto_get_fit_solver(void) { return g_tune.fit_solver.load(); }
+
+int sto_set_tuning(const char* key, int value) {
+    if (!key) return fail(STO_ERR_INVALID, "key is NULL");
+    const std::string k(key);
+    if (k == "fit_split" && (value == 0 || pow2_le32(value))) { g_tune.fit_split = value; return STO_OK; }
+    if (k == "qss_lanes" && (value == 0 || pow2_le32(value))) { g_tune.qss_lanes = value; return STO_OK; }
+    if (k == "qss_group" && (value == 0 || pow2_le32(value))) { g_tune.qss_group = value; return STO_OK; }
+    if (k == "qss_planes" && value >= 0 && value <= 4) { g_tune.qss_planes = value; return STO_OK; }
+    return fail(STO_ERR_INVALID, "unknown tuning key or value");
+}
 int sto_fit_solver_lanes(int M, int B) {
     if (M < 3 || B < 1) return 0;
     return pick_fit_plan(M, B).split;
@@ -932,33 +969,61 @@ int sto_argmin_f64(const double* lap, const int32_t* status, int B, double* best
     return STO_OK;
 }
 
+int sto_argmin_pair_f64(const double* lap, const int32_t* status, int B, int64_t index_base, double* pair,
+                        void* scratch, void* stream) {
+    if (!lap || !pair || !scratch || B < 1) return fail(STO_ERR_INVALID, "bad argmin_pair arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* bl = static_cast<double*>(scratch);
+    long long* bi = reinterpret_cast<long long*>(bl + 1);
+    argmin_kernel<<<1, 1024, 0, st>>>(lap, status, B, bl, bi);
+    argmin_pair_kernel<<<1, 1, 0, st>>>(bl, bi, (long long)index_base, pair);
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
+int sto_argmin_pairs_f64(const double* pairs, int n, double* best_lap, int64_t* best_idx, void* stream) {
+    if (!pairs || !best_lap || !best_idx || n < 1) return fail(STO_ERR_INVALID, "bad argmin_pairs arguments");
+    argmin_pairs_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pairs, n, best_lap,
+                                                                        reinterpret_cast<long long*>(best_idx));
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
+}
+
 // ---- host-buffer entry: the call a ctypes binding makes ---------------------------------------------------
 namespace {
-struct Arena {  // grow-only device arena per device, reused across calls (cudaMalloc is not free)
+// One context per device: a grow-only arena (cudaMalloc is not free), the stream of the *_host entry points and the
+// mutex that serialises callers of THAT device.  Threads driving different GPUs never meet.
+struct HostCtx {
+    std::mutex mu;
     void* p = nullptr;
     size_t n = 0;
-    int dev = -1;
+    cudaStream_t stream = nullptr;
 };
-std::mutex g_arena_mu;
-Arena g_arena;
-cudaStream_t g_host_stream = nullptr;  // stream of the *_host entry points, created once per device
-int g_host_stream_dev = -1;
-int arena_get(int dev, size_t bytes, void** out) {
-    if (g_arena.dev != dev || g_arena.n < bytes) {
-        if (g_arena.p) { cudaSetDevice(g_arena.dev); cudaFree(g_arena.p); g_arena = Arena{}; cudaSetDevice(dev); }
-        STO_CUDA(cudaMalloc(&g_arena.p, bytes));
-        g_arena.n = bytes;
-        g_arena.dev = dev;
+constexpr int kMaxDevices = 64;
+HostCtx g_host[kMaxDevices];
+int arena_get(HostCtx& ctx, size_t bytes, void** out) {   // caller holds ctx.mu and has made the device current
+    if (ctx.n < bytes) {
+        if (ctx.p) { cudaFree(ctx.p); ctx.p = nullptr; ctx.n = 0; }
+        STO_CUDA(cudaMalloc(&ctx.p, bytes));
+        ctx.n = bytes;
     }
-    *out = g_arena.p;
+    *out = ctx.p;
     return STO_OK;
 }
 }  // namespace
 
 int sto_release(void) {
-    std::lock_guard<std::mutex> lk(g_arena_mu);
-    if (g_arena.p) { cudaSetDevice(g_arena.dev); cudaFree(g_arena.p); g_arena = Arena{}; }
-    if (g_host_stream) { cudaSetDevice(g_host_stream_dev); cudaStreamDestroy(g_host_stream); g_host_stream = nullptr; g_host_stream_dev = -1; }
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < kMaxDevices; ++d) {
+        HostCtx& ctx = g_host[d];
+        std::lock_guard<std::mutex> lk(ctx.mu);
+        if (!ctx.p && !ctx.stream) continue;
+        cudaSetDevice(d);
+        if (ctx.p) { cudaFree(ctx.p); ctx.p = nullptr; ctx.n = 0; }
+        if (ctx.stream) { cudaStreamDestroy(ctx.stream); ctx.stream = nullptr; }
+    }
+    if (have_cur) cudaSetDevice(cur);
     return STO_OK;
 }
 
@@ -971,7 +1036,9 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
     if (!centre_x || !centre_y || !normal_x || !normal_y || !ts || !offsets_host || !lap_host || !status_host)
         return fail(STO_ERR_INVALID, "NULL argument");
     if (int rc = check_vehicle(vehicle)) return rc;
-    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (device < 0 || device >= kMaxDevices) return fail(STO_ERR_INVALID, "device index out of range");
+    HostCtx& ctx = g_host[device];
+    std::lock_guard<std::mutex> lk(ctx.mu);
     STO_CUDA(cudaSetDevice(device));
     // chunk size: the largest multiple of 32 candidates whose buffers fit the budget
     auto need = [&](int bc) {
@@ -982,18 +1049,18 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
     size_t budget = max_work_bytes ? max_work_bytes : (size_t)32 << 30;
     // Steady state (same shape as the previous call: the cached arena already holds the whole batch) touches no
     // driver-wide state: no cudaMemGetInfo, no allocation, no stream creation.
-    const bool arena_fits = g_arena.dev == device && g_arena.n >= need(B) && need(B) <= budget;
+    const bool arena_fits = ctx.n >= need(B) && need(B) <= budget;
     if (!arena_fits) {
         size_t free_b = 0, total_b = 0;
         STO_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t avail = free_b + ((g_arena.dev == device) ? g_arena.n : 0);
+        size_t avail = free_b + ctx.n;
         if (budget > avail / 10 * 8) budget = avail / 10 * 8;
     }
     int bc = B;
     while (bc > 32 && need(bc) > budget) bc = ((bc / 2) + 31) & ~31;
     if (need(bc) > budget) return fail(STO_ERR_WORKSPACE, "device memory budget too small for 32 candidates");
     void* base = nullptr;
-    if (int rc = arena_get(device, need(bc), &base)) return rc;
+    if (int rc = arena_get(ctx, need(bc), &base)) return rc;
     const size_t ld = ldof(bc);
     Carver c(base);
     double* d_cx = c.take<double>(M); double* d_cy = c.take<double>(M);
@@ -1005,12 +1072,8 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
     int32_t* d_status = c.take<int32_t>(ld);
     void* d_work = c.take<char>(sto_lap_workspace_bytes(M, N, bc, impl));
     const size_t work_bytes = sto_lap_workspace_bytes(M, N, bc, impl);
-    if (g_host_stream_dev != device) {
-        if (g_host_stream) { cudaStreamDestroy(g_host_stream); g_host_stream = nullptr; }
-        STO_CUDA(cudaStreamCreateWithFlags(&g_host_stream, cudaStreamNonBlocking));
-        g_host_stream_dev = device;
-    }
-    cudaStream_t st = g_host_stream;
+    if (!ctx.stream) STO_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    cudaStream_t st = ctx.stream;
     int rc = STO_OK;
     auto H2D = [&](void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st); };
     cudaError_t e = H2D(d_cx, centre_x, sizeof(double) * M);

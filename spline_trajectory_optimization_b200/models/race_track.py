@@ -13,18 +13,20 @@ from .trajectory import BSplineTrajectory, Trajectory
 
 class RaceTrack:
     def __init__(self, name: str, left: np.ndarray, right: np.ndarray, centerline: np.ndarray, s=10.0, interval=2.0,
-                 arc_length: bool = False) -> None:
+                 arc_length: bool = False, device: bool = True) -> None:
         """arc_length=True also fills DIST_TO_SF_* of the three discretisations with the reference's adaptive
-        quadrature (seconds per line; the evaluator does not need it)."""
+        quadrature (seconds per line; the evaluator does not need it).  device=False keeps the whole construction on
+        the host (SciPy evaluation, NumPy bound look-up): no CUDA library is loaded."""
+        self._device = device
         assert left.shape[0] >= 3 and right.shape[0] >= 3
         assert left.shape[1] >= 2 and right.shape[1] >= 2
         self.name = name
         self.left_s = BSplineTrajectory(left[:, :2], s, 3)
         self.right_s = BSplineTrajectory(right[:, :2], s, 3)
         self.center_s = BSplineTrajectory(centerline[:, :2], s, 3)
-        self.left_d = self.left_s.sample_along(interval, arc_length=arc_length)
-        self.right_d = self.right_s.sample_along(interval, arc_length=arc_length)
-        self.center_d = self.center_s.sample_along(interval, arc_length=arc_length)
+        self.left_d = self.left_s.sample_along(interval, arc_length=arc_length, device=device)
+        self.right_d = self.right_s.sample_along(interval, arc_length=arc_length, device=device)
+        self.center_d = self.center_s.sample_along(interval, arc_length=arc_length, device=device)
         # closed boundary polylines (what the reference wraps in shapely LinearRings, :31-33)
         self.left_r = self.left_d[:, :2].copy()
         self.right_r = self.right_d[:, :2].copy()
@@ -45,7 +47,7 @@ class RaceTrack:
 
     def fill_trajectory_boundaries(self, traj: Trajectory):
         """Fills LEFT/RIGHT_BOUND_X/Y of ``traj`` in place (normal-ray look-up, max_dist = 100 m)."""
-        traj.fill_bounds(self.left_r, self.right_r, max_dist=100.0)
+        traj.fill_bounds(self.left_r, self.right_r, max_dist=100.0, device=self._device)
 
     def left_normals(self):
         """Unit left normal (-sin yaw, cos yaw) at every centre sample."""

@@ -55,3 +55,35 @@ def all_gather_laps(local_laps, B, group=None):
     out = torch.empty(world * width, dtype=local_laps.dtype, device=local_laps.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
+
+class DeviceArgmin:
+    """The same reduction on the GPU with three small kernels of the library and ONE collective of 16 bytes per rank
+    (`global_argmin` above spends ~10 eager torch launches on it): local argmin over the shard -> {lap, global index}
+    pair (sto_argmin_pair_f64) -> ncclAllGather of the pairs -> argmin over the pairs (sto_argmin_pairs_f64).  Buffers
+    are allocated once; nothing synchronises.  Identical on every rank, ties to the lowest global index."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib_mod, self.lib = C, _lib, _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.pair = torch.empty(2, dtype=torch.float64, device=device)
+        self.scratch = torch.empty(2, dtype=torch.float64, device=device)
+        self.gathered = torch.empty(2 * self.world, dtype=torch.float64, device=device)
+        self.best = torch.empty(1, dtype=torch.float64, device=device)
+        self.idx = torch.empty(1, dtype=torch.int64, device=device)
+
+    def __call__(self, lap, status, shard_lo):
+        """lap[B], status[B] (or None): this rank's shard (device).  Returns (best_lap[1], best_global_idx[1])."""
+        C, chk = self._C, self._lib_mod.check
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        chk(self.lib.sto_argmin_pair_f64(p(lap), p(status), lap.numel(), int(shard_lo), p(self.pair), p(self.scratch), st))
+        src = self.pair
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.pair, group=self.group)
+            src = self.gathered
+        chk(self.lib.sto_argmin_pairs_f64(p(src), self.world, p(self.best), p(self.idx), st))
+        return self.best, self.idx

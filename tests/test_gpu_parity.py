@@ -236,7 +236,7 @@ def test_simulator_drop_in(sto):
                  (Trajectory.DIST_TO_SF_FWD, "in_DIST_FWD"), (Trajectory.BANK, "in_BANK")):
         traj[:, c] = d[k]
     before = traj.points.copy()
-    res = Simulator(Vehicle(test_vehicle_params())).run_simulation(traj, False)
+    res = Simulator(Vehicle(test_vehicle_params()), track_iteration_flag=True).run_simulation(traj, False)
     assert np.array_equal(traj.points, before)                        # input untouched (simulator.py:64)
     out = res.trajectory
     assert rel_err(out[:, Trajectory.SPEED], d["out_SPEED"]) < 1e-12
@@ -250,8 +250,10 @@ def test_simulator_drop_in(sto):
     assert np.allclose(got, ref, rtol=1e-11, atol=0)
     assert abs(res.lap_time - float(d["lap"])) < 1e-9
     assert "Lap Time" in str(res)
-    # the fast variant (memoised kernel): same profile bit for bit, ITERATION_FLAG not tracked
-    fast = Simulator(Vehicle(test_vehicle_params()), track_iteration_flag=False).run_simulation(traj, False)
+    # the default (memoised kernel): same profile bit for bit, ITERATION_FLAG (debug column) not tracked
+    fast = Simulator(Vehicle(test_vehicle_params())).run_simulation(traj, False)
+    assert np.allclose([fast.total_time, fast.average_speed, fast.max_speed, fast.min_speed, fast.max_lat_acc,
+                        fast.max_lon_acc, fast.max_lon_dcc], ref, rtol=1e-11, atol=0)
     for c in (Trajectory.SPEED, Trajectory.LON_ACC, Trajectory.LAT_ACC, Trajectory.TIME):
         assert np.array_equal(fast.trajectory[:, c], out[:, c])
     assert (fast.trajectory[:, Trajectory.ITERATION_FLAG] == -1).all() and fast.lap_time == res.lap_time
@@ -348,6 +350,37 @@ def test_full_size_properties(sto):
     assert np.array_equal(lap_plain.cpu().numpy(), lap[:256])
 
 
+def test_full_size_parity_512_candidates(sto):
+    """BASELINE configs[1] at its stated size (M = N = 2895, a 4,096-candidate launch): every 8th candidate - 512 lines -
+    against the oracle.  ref_pow = 0 (the kernels' x*x arithmetic): laps BIT-EXACT.  ref_pow = 1 (the reference's libm
+    pow(x, 2), the arithmetic the goldens pin bit for bit): |lap difference| <= 1e-6 s, BASELINE's lap tolerance, asserted
+    (measured ~2.5e-10 s)."""
+    import os
+    from spline_trajectory_optimization_b200 import candidates, tracks
+    from spline_trajectory_optimization_b200.models.race_track import RaceTrack
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    c, l, r = tracks.monza_raw()
+    rt = RaceTrack("monza", l, r, c, s=10.0, interval=2.0)
+    M, B = len(rt.center_d), 4096
+    off = candidates.smooth_offsets(M, B, rt.dist_to_left, rt.dist_to_right, seed=4321)
+    ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), Vehicle(test_vehicle_params()))
+    lap, st = ev.lap_times(ev.to_sample_major(torch.from_numpy(off).cuda()), B=B)
+    lap, st = lap.cpu().numpy(), st.cpu().numpy()
+    assert not st.any()
+    pick = np.arange(0, B, 8)
+    assert len(pick) == 512
+    g = golden("cand_m2895_n2895")
+    ov = O.make_vehicle(*veh_args(g))
+    nrm = rt.left_normals()
+    threads = min(32, os.cpu_count() or 1)
+    args = (rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off[pick], rt.center_d.ts(), np.zeros(M), ov)
+    olap0, ost0 = O.lap_batch(*args, n_threads=threads, ref_pow=0)
+    assert not ost0.any() and np.array_equal(lap[pick], olap0)
+    olap1, ost1 = O.lap_batch(*args, n_threads=threads, ref_pow=1)
+    assert not ost1.any()
+    assert np.max(np.abs(lap[pick] - olap1)) <= 1e-6, np.max(np.abs(lap[pick] - olap1))
+
+
 def test_fused_banked_oval(sto):
     """BASELINE config 4 (bank-aware QSS through the fused path): synthetic banked oval, 4-column centre line, bank
     carried to the samples by index; bit-exact against the oracle."""
@@ -439,14 +472,14 @@ def test_fit_partitioned_on_device(sto):
             assert lib.sto_fit_solver_lanes(M, 1 << 20) == 1 and lib.sto_fit_solver_lanes(100, 4) == 1
             try:
                 for lanes in (32, 16, 8, 4, 2, 1):
-                    os.environ["STO_FIT_SPLIT"] = str(lanes)
+                    _lib.check(lib.sto_set_tuning(b"fit_split", lanes))
                     u, cx, cy, st = ev.fit(to_sm(d["offsets"]), B=B)
                     torch.cuda.synchronize()
                     assert not st[:B].any()
                     u, cx, cy = to_cm(u, B), to_cm(cx, B), to_cm(cy, B)
                     assert np.array_equal(u, hu) and np.array_equal(cx, hcx) and np.array_equal(cy, hcy), lanes
             finally:
-                del os.environ["STO_FIT_SPLIT"]
+                _lib.check(lib.sto_set_tuning(b"fit_split", 0))
             lap1, st1 = ev.lap_times(to_sm(d["offsets"]), B=B)
         with fit_solver("thomas"):
             u0, cx0, cy0, _ = ev.fit(to_sm(d["offsets"]), B=B)

@@ -27,7 +27,7 @@ if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_benc
         off = to_sm(np.tile(base, ((B + 63) // 64, 1))[:B])
         line = f"M={M} B={B:6d}"
         for mode, lanes in ((2, 1), (2, 4), (2, 8), (2, 16), (2, 32), (0, 1), (0, 2), (0, 8), (1, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)):
-            os.environ["STO_FIT_SPLIT"] = str(lanes)
+            lib.sto_set_tuning(b"fit_split", lanes)
             lib.sto_set_fit_solver(mode)
             best = 1e9
             for it in range(3):
@@ -39,7 +39,7 @@ if os.environ.get("SWEEP"):   # explicit lane counts: python tools/fit_part_benc
                 best = min(best, e0.elapsed_time(e1))
             line += f"  {('thomas', 'blocks', 'fitpack')[mode]}x{lanes}: {best:8.2f} ms"
         print(line, flush=True)
-    del os.environ["STO_FIT_SPLIT"]
+    lib.sto_set_tuning(b"fit_split", 0)
     lib.sto_set_fit_solver(2)
     sys.exit(0)
 for B in (1, 64, 1024, 4096, 16384):

@@ -14,7 +14,7 @@ for B in (4096, 32768):
     d_off = ev.to_sample_major(torch.from_numpy(np.tile(off, (B // 4096, 1))).cuda())
     ref = None
     for split in (1, 2, 4, 8, 16, 32):
-        os.environ["STO_FIT_SPLIT"] = str(split)
+        lib.sto_set_tuning(b"fit_split", split)
         lib.sto_set_stage_timing(1)
         best = 1e9
         for _ in range(3):

@@ -25,9 +25,9 @@ for B, lanes, planes, group in configs:
             off = np.tile(off, (B // 4096, 1))
         cache[B] = (ev, ev.to_sample_major(torch.from_numpy(off).cuda()))
     ev, d_off = cache[B]
-    os.environ["STO_QSS_LANES"] = str(lanes)
-    os.environ["STO_QSS_PLANES"] = planes
-    os.environ["STO_QSS_GROUP"] = group
+    _lib.check(lib.sto_set_tuning(b"qss_lanes", int(lanes)))
+    _lib.check(lib.sto_set_tuning(b"qss_planes", {"s": 1, "g": 2, "g0": 3, "g1": 4}[planes]))
+    _lib.check(lib.sto_set_tuning(b"qss_group", int(group)))
     lib.sto_set_stage_timing(1)
     best = None
     for it in range(3):
