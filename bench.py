@@ -277,6 +277,72 @@ def nccl_log_report(d, world):
     return {"ranks_seen": len(ranks), "nranks": world, "nvls_mentioned": nvls, "log_dir": d}
 
 
+def fast_mode_leg(ev, d_small, B, exact_lap, rt, peak, big=131072):
+    """The separately-reported FAST MODE (sto_lap_time_fast_f64: Thomas fit + sampler + two-sweep QSS + fill_time in one
+    kernel): throughput lap-only and with every output column materialised, at the headline batch and at a large one;
+    achieved HBM GB/s on ALGORITHMIC bytes against the measured peak; its measured lap error against the exact schedule
+    on the same lines; and the track-table staging (bulk copy into shared memory) against warp-uniform global loads."""
+    import torch
+    from spline_trajectory_optimization_b200 import candidates
+    M, N, dev = ev.M, ev.N, ev.device
+    alg_lap = 8 * M + 8                                     # offsets in, lap out
+    alg_full = 8 * M + 8 + 16 * (M + 3) + 64 * N            # + coefficients + 8 sample columns (SURVEY.md 8d)
+
+    def timed(off, nb, reps, **kw):
+        ev.lap_times_fast(off, B=nb, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = ev.lap_times_fast(off, B=nb, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    out = {"api": "sto_lap_time_fast_f64", "rounds": 2,
+           "algorithmic_bytes_per_candidate": {"lap_only": alg_lap, "full_outputs": alg_full},
+           "note": "NOT the reference's result: two sweeps with the reference's step operator instead of its lock-step "
+                   "multi-front schedule; reported separately, never the default"}
+    ms, r = timed(d_small, B, 5, rounds=2)
+    fast_lap = r[0].cpu().numpy()
+    err = fast_lap - exact_lap
+    order_f, order_e = np.argsort(fast_lap), np.argsort(exact_lap)
+    rank_f = np.empty(B); rank_f[order_f] = np.arange(B)
+    rank_e = np.empty(B); rank_e[order_e] = np.arange(B)
+    out["error_vs_exact_schedule"] = {
+        "candidates": int(B), "max_abs_lap_err_s": float(np.max(np.abs(err))), "mean_lap_err_s": float(np.mean(err)),
+        "std_lap_err_s": float(np.std(err)), "spearman_rank_correlation": float(np.corrcoef(rank_f, rank_e)[0, 1]),
+        "exact_best_is_in_fast_top": int(rank_f[order_e[0]]) + 1}
+    out["max_abs_lap_err_s"] = out["error_vs_exact_schedule"]["max_abs_lap_err_s"]
+    ms_g, _ = timed(d_small, B, 5, rounds=2, stage_tables=0)
+    ms_f, _ = timed(d_small, B, 3, rounds=2, outputs=True)
+    out["batch_%d" % B] = {"ms_lap_only": ms, "value_lap_only": B / (ms * 1e-3), "ms_full_outputs": ms_f,
+                           "value_full_outputs": B / (ms_f * 1e-3), "unit": UNIT,
+                           "ms_lap_only_tables_in_global_memory": ms_g}
+    free_b, _tot = torch.cuda.mem_get_info(dev)
+    per_cand = ev.lib.sto_fast_workspace_bytes(M, N, 1024) / 1024.0 + 8.0 * (2 * (M + 3) + 8 * N) + 8.0 * M
+    BL = int(min(big, (int(0.6 * free_b / per_cand) // 32) * 32))
+    d_l = candidates.smooth_offsets_device(M, 0, BL, rt.dist_to_left, rt.dist_to_right, dev, seed=77)
+    ms_l, r_l = timed(d_l, BL, 2, rounds=2)
+    ms_lg, _ = timed(d_l, BL, 2, rounds=2, stage_tables=0)
+    ms_lf, r_lf = timed(d_l, BL, 2, rounds=2, outputs=True)
+    ok = bool((r_l[1] == 0).all().item()) and bool(torch.equal(r_l[0], r_lf[0]))
+    del d_l, r_lf
+    out["batch_%d" % BL] = {"ms_lap_only": ms_l, "value_lap_only": BL / (ms_l * 1e-3), "ms_full_outputs": ms_lf,
+                            "value_full_outputs": BL / (ms_lf * 1e-3), "unit": UNIT,
+                            "ms_lap_only_tables_in_global_memory": ms_lg, "all_status_ok_and_laps_equal": ok}
+    ach_lap = alg_lap * BL / (ms_l * 1e-3) / 1e9
+    ach_full = alg_full * BL / (ms_lf * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "kernel": "fast_kernel", "peak": peak, "unit": "GB/s",
+                       "achieved": ach_full, "frac": ach_full / peak, "counted_on": "full outputs, batch %d" % BL,
+                       "achieved_lap_only": ach_lap, "frac_lap_only": ach_lap / peak, "traffic": None,
+                       "note": "lap-only the path is ~70 flop per algorithmic byte (FP64-pipe side of the 5.7 flop/B "
+                               "balance point); with the outputs materialised ~6 flop/B"}
+    out["table_staging"] = {"how": "cp.async.bulk (UBLKCP) + mbarrier, six tables once per CTA into shared memory",
+                            "speedup_small_batch": ms_g / ms, "speedup_large_batch": ms_lg / ms_l}
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -572,6 +638,8 @@ def run_gpu_arm(args):
                                "note": "262,144 / 8 candidates in one launch; bit planes move to global memory at this "
                                        "size (DESIGN.md section 2)"}
         del d_l
+    if world == 1 and cfg == 1 and not args.no_fast_mode:
+        line["fast_mode"] = fast_mode_leg(ev, d_off[0][0], B, lap_host, rt, peak)
     if not args.no_cpu_baseline and world == 1:
         base_off = host_first if not strong else d_off[0][0][:, :min(B, 4096)].T.contiguous().cpu().numpy()
         cb, olap = cpu_baseline_leg(O, ov, rt, base_off)
@@ -598,6 +666,7 @@ def main():
     ap.add_argument("--launch-gb", type=float, default=56.0, help="device workspace budget of one launch")
     ap.add_argument("--parity", type=int, default=0, help="candidates checked against the oracle (0 = choose)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the separately-reported fast-mode block")
     ap.add_argument("--large-batch", type=int, default=32768,
                     help="config 1, N = 1: also report device-resident throughput at this batch size (0 = skip)")
     args = ap.parse_args()

@@ -140,6 +140,22 @@ def qss(X, Y, R, sinb, veh, ref_pow=1):
                 steps=stats[0], iters=stats[1], spawned=stats[2], peak_rows=stats[3], effective=stats[4])
 
 
+def qss_sweep(X, Y, R, sinb, veh, rounds=2, ref_pow=0):
+    """FAST-MODE checker (not the reference's algorithm): `rounds` x (backward lap, forward lap) with the reference's
+    step operator, the CPU twin of the library's sto_lap_time_fast_f64."""
+    X, Y, R, sinb = _f64(X), _f64(Y), _f64(R), _f64(sinb)
+    N = len(X)
+    v, a, lat, tseg = (np.empty(N) for _ in range(4))
+    lap = C.c_double()
+    L = lib()
+    L.sto_oracle_qss_sweep.restype = C.c_int
+    L.sto_oracle_qss_sweep.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.POINTER(OracleVehicle), C.c_int, _dp, _dp, _dp, _dp,
+                                       C.POINTER(C.c_double), C.c_int]
+    rc = L.sto_oracle_qss_sweep(_p(X), _p(Y), _p(R), _p(sinb), N, C.byref(veh), int(rounds), _p(v), _p(a), _p(lat),
+                                _p(tseg), C.byref(lap), int(ref_pow))
+    return dict(status=rc, v=v, a=a, lat=lat, time=tseg, lap=lap.value)
+
+
 def lap_batch(centre_x, centre_y, normal_x, normal_y, offsets, ts, sinb, veh, n_threads=1, ref_pow=1):
     """offsets[B, M] (candidate-major, host).  Returns lap[B], status[B]."""
     cx, cy, nx, ny = _f64(centre_x), _f64(centre_y), _f64(normal_x), _f64(normal_y)

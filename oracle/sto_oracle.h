@@ -36,6 +36,10 @@ int sto_oracle_sample(const double* t, int nt, const double* cx, const double* c
 int sto_oracle_qss(const double* X, const double* Y, const double* R, const double* sinb, int N,
                    const sto_oracle_vehicle* V, double* v, double* a, double* lat, double* flag,
                    double* tseg, double* lap, int64_t* stats, int ref_pow);
+/* fast-mode checker (not the reference's algorithm; see sto_oracle.c) */
+int sto_oracle_qss_sweep(const double* X, const double* Y, const double* R, const double* sinb, int N,
+                         const sto_oracle_vehicle* V, int rounds, double* v, double* a, double* lat, double* tseg,
+                         double* lap, int ref_pow);
 int sto_oracle_lap_from_offsets(const double* centre_x, const double* centre_y, const double* normal_x,
                                 const double* normal_y, const double* offsets, int M, const double* ts,
                                 const double* sinb, int N, const sto_oracle_vehicle* V, double* lap,

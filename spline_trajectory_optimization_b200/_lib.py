@@ -29,6 +29,11 @@ class StoProfileOut(C.Structure):
     _fields_ = [("speed", _vp), ("lon_acc", _vp), ("lat_acc", _vp), ("time", _vp), ("owner", _vp)]
 
 
+class StoFastOut(C.Structure):
+    """sto_fast_out_f64"""
+    _fields_ = [(k, _vp) for k in ("cx", "cy", "x", "y", "yaw", "radius", "speed", "lon_acc", "lat_acc", "time")]
+
+
 class StoError(RuntimeError):
     pass
 
@@ -60,6 +65,9 @@ _SIGNATURES = {
     "sto_fit_lsq_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "sto_fit_periodic_lsq_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 3 + [_vp, C.c_int, C.c_int] + [_vp] * 5 +
                                  [C.c_size_t, _vp]),
+    "sto_fast_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "sto_lap_time_fast_f64": (C.c_int, [_vp] * 7 + [C.c_int] * 4 + [C.POINTER(StoVehicle), C.c_int, _vp, _vp, _vp, _vp,
+                                        C.c_size_t, C.c_int, _vp]),
     "sto_set_stage_timing": (C.c_int, [C.c_int]),
     "sto_set_fit_solver": (C.c_int, [C.c_int]),
     "sto_get_fit_solver": (C.c_int, []),

@@ -13,6 +13,7 @@
 
 #include "sto_common.cuh"
 #include "sto_eval.cuh"
+#include "sto_fast.cuh"
 #include "sto_fit.cuh"
 #include "sto_fit_lsq.cuh"
 #include "sto_qss.cuh"
@@ -313,6 +314,61 @@ __global__ void qss_memo_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const 
     int32_t* ring = reinterpret_cast<int32_t*>(sto_planes + (size_t)6 * W.W * cpw);
     const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, ring, 32, lane, A.N, W.W);
     sto::qss_memo_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G);
+}
+
+// ---- fast mode (sto_fast.cuh): one kernel, one candidate per thread ------------------------------------------------
+// STAGE: the six track tables are copied once per CTA into shared memory by the bulk-copy engine (cp.async.bulk with an
+// mbarrier transaction count - the 1-D TMA path; SASS UBLKCP) and every lane reads them from there as broadcasts.
+struct FastTables { int n_cen, n_ts; bool have_sinb; };
+extern __shared__ __align__(16) double sto_fast_smem[];
+template <bool STAGE>
+__global__ void fast_kernel(sto::FastArgs Ain, FastTables T, const __grid_constant__ sto_vehicle_f64 V) {
+    sto::FastArgs A = Ain;
+    if (STAGE) {
+        __shared__ __align__(8) unsigned long long bar;
+        const int pc = (T.n_cen + 1) & ~1, pt = (T.n_ts + 1) & ~1;        // table strides: multiples of 16 bytes
+        double* s_cenx = sto_fast_smem;
+        double* s_ceny = s_cenx + pc;
+        double* s_nrmx = s_ceny + pc;
+        double* s_nrmy = s_nrmx + pc;
+        double* s_ts = s_nrmy + pc;
+        double* s_sb = s_ts + pt;
+        const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bc = (unsigned)(T.n_cen / 2) * 16u, bt = (unsigned)(T.n_ts / 2) * 16u;   // whole 16-byte units
+            const unsigned total = 4u * bc + bt + (T.have_sinb ? bt : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+            const double* src[6] = {Ain.F.cenx, Ain.F.ceny, Ain.F.nrmx, Ain.F.nrmy, Ain.E.ts, Ain.Q.sinb};
+            double* dst[6] = {s_cenx, s_ceny, s_nrmx, s_nrmy, s_ts, s_sb};
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const unsigned nb = (k < 4) ? bc : bt;
+                if (nb == 0u || (k == 5 && !T.have_sinb)) continue;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(dst[k])), "l"(src[k]), "r"(nb), "r"(bar_s) : "memory");
+                const int n = (k < 4) ? T.n_cen : T.n_ts;
+                if (n & 1) dst[k][n - 1] = src[k][n - 1];                   // odd tail element: a plain copy
+            }
+        }
+        {   // every thread waits for the transaction count (phase 0)
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar_s) : "memory");
+        }
+        __syncthreads();   // the tail elements stored by thread 0
+        A.F.cenx = s_cenx; A.F.ceny = s_ceny; A.F.nrmx = s_nrmx; A.F.nrmy = s_nrmy;
+        A.E.ts = s_ts;
+        if (T.have_sinb) A.Q.sinb = s_sb;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < A.Q.B;
+    sto::fast_candidate(A, V, active ? t : A.Q.B - 1, active, threadIdx.x & ~31);
 }
 
 // FP64 pipe peak for the roofline report: 8 independent DFMA chains per thread, every SM full.
@@ -891,6 +947,87 @@ int sto_lap_time_splines_f64(const double* t, int nt, int k, const double* cx, c
     A.sp_ent = w.sp_ent; A.sp_ext = w.sp_ext; A.sp_turn = w.sp_turn; A.sp_flag = w.sp_flag;
     A.lap = lap; A.status = status;
     return launch_qss(A, w, vehicle, impl, false, st);
+}
+
+// ---- fast mode ------------------------------------------------------------------------------------------------------
+struct FastWork { double *u, *cx, *cy, *R, *dd, *df, *v, *a; FitWork fit; };
+static FastWork carve_fast(Carver& c, int M, int N, size_t ld) {
+    FastWork w;
+    w.u = c.take<double>((size_t)(M + 1) * ld);
+    w.cx = c.take<double>((size_t)(M + 3) * ld);
+    w.cy = c.take<double>((size_t)(M + 3) * ld);
+    w.R = c.take<double>((size_t)N * ld);
+    w.dd = c.take<double>((size_t)N * ld);
+    w.df = c.take<double>((size_t)N * ld);
+    w.v = c.take<double>((size_t)N * ld);
+    w.a = c.take<double>((size_t)N * ld);
+    w.fit.cp = c.take<double>((size_t)M * ld);
+    w.fit.zx = c.take<double>((size_t)M * ld);
+    w.fit.zy = c.take<double>((size_t)M * ld);
+    w.fit.zz = c.take<double>((size_t)M * ld);
+    w.fit.ze = nullptr;   // FITPACK solver only
+    return w;
+}
+
+size_t sto_fast_workspace_bytes(int M, int N, int B) {
+    if (M < 3 || N < 2 || B < 1) return 0;
+    Carver c(nullptr);
+    carve_fast(c, M, N, ldof(B));
+    return c.bytes();
+}
+
+int sto_lap_time_fast_f64(const double* centre_x, const double* centre_y, const double* normal_x,
+                          const double* normal_y, const double* sin_bank, const double* ts, const double* offsets,
+                          int M, int N, int B, int ld, const sto_vehicle_f64* vehicle, int rounds,
+                          const sto_fast_out_f64* out, double* lap, int32_t* status, void* work, size_t work_bytes,
+                          int stage_tables, void* stream) {
+    if (M < 3 || N < 2 || B < 1 || ld < B || rounds < 1) return fail(STO_ERR_INVALID, "bad sizes");
+    if (!centre_x || !centre_y || !normal_x || !normal_y || !ts || !offsets || !lap || !status || !work)
+        return fail(STO_ERR_INVALID, "NULL argument");
+    if ((size_t)ld != ldof(B)) return fail(STO_ERR_INVALID, "sto_lap_time_fast_f64 needs ld == round_up(B, 32)");
+    if (int rc = check_vehicle(vehicle)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(work);
+    FastWork w = carve_fast(c, M, N, (size_t)ld);
+    if (c.bytes() > work_bytes) return fail(STO_ERR_WORKSPACE, "fast-mode workspace too small");
+    sto::FastArgs A{};
+    A.rounds = rounds;
+    sto::FitArgs& F = A.F;
+    F.cenx = centre_x; F.ceny = centre_y; F.nrmx = normal_x; F.nrmy = normal_y; F.off = offsets;
+    F.M = M; F.B = B; F.ld = ld; F.status = status;
+    F.u = w.u; F.cx = (out && out->cx) ? out->cx : w.cx; F.cy = (out && out->cy) ? out->cy : w.cy;
+    F.cp = w.fit.cp; F.zx = w.fit.zx; F.zy = w.fit.zy; F.zz = w.fit.zz; F.ze = nullptr;
+    A.E = sto::EvalArgs{F.u, F.cx, F.cy, ts, M, N, B, ld, out ? out->x : nullptr, out ? out->y : nullptr,
+                        out ? out->yaw : nullptr, (out && out->radius) ? out->radius : w.R, w.dd, w.df};
+    sto::QssArgs& Q = A.Q;
+    Q.dd = w.dd; Q.df = w.df; Q.R = A.E.radius; Q.sinb = sin_bank; Q.N = N; Q.B = B; Q.ld = ld;
+    Q.v = (out && out->speed) ? out->speed : w.v;
+    Q.a = (out && out->lon_acc) ? out->lon_acc : w.a;
+    Q.lat = out ? out->lat_acc : nullptr;
+    Q.tseg = out ? out->time : nullptr;
+    Q.lap = lap; Q.status = status;
+    // Track tables in shared memory (one bulk copy per table and CTA) when they fit and are 16-byte aligned.
+    const size_t pc = (size_t)((M + 1) & ~1), pt = (size_t)((N + 1) & ~1);
+    const size_t smem = (4 * pc + 2 * pt) * sizeof(double);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool can_stage = smem <= kMemoSmemBudget && al16(centre_x) && al16(centre_y) && al16(normal_x) &&
+                           al16(normal_y) && al16(ts) && (!sin_bank || al16(sin_bank));
+    if (stage_tables > 0 && !can_stage)
+        return fail(STO_ERR_INVALID, "track tables cannot be staged (need 16-byte aligned pointers and <= 200 KB in all)");
+    const bool stage = (stage_tables != 0) && can_stage;
+    FastTables T{M, N, sin_bank != nullptr};
+    if (stage) {
+        // one CTA per SM (the tables take most of its shared memory): as many threads as the batch gives each SM
+        int block = ((B + 147) / 148 + 31) & ~31;
+        block = block < 32 ? 32 : (block > 512 ? 512 : block);
+        STO_CUDA(cudaFuncSetAttribute(fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fast_kernel<true><<<grid_for(B, block), block, smem, st>>>(A, T, *vehicle);
+    } else {
+        const int block = pick_block(B);
+        fast_kernel<false><<<grid_for(B, block), block, 0, st>>>(A, T, *vehicle);
+    }
+    STO_CUDA(cudaGetLastError());
+    return STO_OK;
 }
 
 int sto_set_stage_timing(int on) {

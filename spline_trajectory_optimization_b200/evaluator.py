@@ -187,6 +187,34 @@ class BatchedLineEvaluator:
                 _ptr(lap), _ptr(st), _ptr(work), work.numel(), _stream()))
         return lap[:B], st[:B]
 
+    def lap_times_fast(self, offsets_sm, B=None, rounds=2, outputs=False, stage_tables=-1, out=None, status=None):
+        """FAST MODE (separately reported, NOT the reference's result): fit + sampler + a two-sweep QSS with the
+        reference's step operator + fill_time in ONE kernel (sto_lap_time_fast_f64, csrc/sto_fast.cuh).  Laps differ from
+        `lap_times` (the exact schedule) by 0.005 .. 3 s: use it to rank candidates, then score the short list exactly.
+        outputs=True also materialises cx, cy [M+3, ld] and x, y, yaw, radius, speed, lon_acc, lat_acc, time [N, ld].
+        Returns (lap[B], status[B]) or (lap, status, dict of outputs)."""
+        M, ld = offsets_sm.shape
+        B = ld if B is None else int(B)
+        assert M == self.M and offsets_sm.dtype == torch.float64 and offsets_sm.is_contiguous()
+        assert ld == round_up32(B), "leading dimension must be round_up(B, 32)"
+        with torch.cuda.device(self.device):
+            lap = out if out is not None else torch.empty(ld, dtype=torch.float64, device=self.device)
+            st = status if status is not None else torch.empty(ld, dtype=torch.int32, device=self.device)
+            res, fo = None, None
+            if outputs:
+                res = {k: torch.empty((M + 3, ld), dtype=torch.float64, device=self.device) for k in ("cx", "cy")}
+                res.update({k: torch.empty((self.N, ld), dtype=torch.float64, device=self.device)
+                            for k in ("x", "y", "yaw", "radius", "speed", "lon_acc", "lat_acc", "time")})
+                fo = _lib.StoFastOut(**{k: v.data_ptr() for k, v in res.items()})
+            nbytes = self.lib.sto_fast_workspace_bytes(self.M, self.N, B)
+            work = self._workspace(nbytes)
+            _lib.check(self.lib.sto_lap_time_fast_f64(
+                _ptr(self.d["cx"]), _ptr(self.d["cy"]), _ptr(self.d["nx"]), _ptr(self.d["ny"]), _ptr(self.d_sinb),
+                _ptr(self.d_ts), _ptr(offsets_sm), self.M, self.N, B, ld, C.byref(self.vehicle), int(rounds),
+                None if fo is None else C.byref(fo), _ptr(lap), _ptr(st), _ptr(work), work.numel(), int(stage_tables),
+                _stream()))
+        return (lap[:B], st[:B]) if res is None else (lap[:B], st[:B], res)
+
     def to_sample_major(self, offsets_cm):
         """[B, M] candidate-major CUDA tensor -> [M, round_up(B, 32)] sample-major (device transpose kernel)."""
         B, M = offsets_cm.shape

@@ -12,6 +12,7 @@
 #include "../../spline_trajectory_optimization_b200/csrc/sto_common.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_eval.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_fit.cuh"
+#include "../../spline_trajectory_optimization_b200/csrc/sto_fast.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_fit_lsq.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss_memo.cuh"
@@ -143,6 +144,33 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
             }
         }
     }
+    return 0;
+}
+
+// fast mode (sto_fast.cuh): offsets [M][ld] -> lap[B]; optional v, a, tseg [N][ld]
+int hostsim_fast(const double* cenx, const double* ceny, const double* nrmx, const double* nrmy, const double* sinb,
+                 const double* ts, const double* off, int M, int N, int B, int ld, const sto_vehicle_f64* V, int rounds,
+                 double* v, double* a, double* tseg, double* lap, int32_t* status) {
+    std::vector<double> w(((size_t)(M + 1) + 2 * (size_t)(M + 3) + 3 * (size_t)N + 4 * (size_t)M) * ld);
+    double* p = w.data();
+    sto::FastArgs A{};
+    A.rounds = rounds;
+    A.F.cenx = cenx; A.F.ceny = ceny; A.F.nrmx = nrmx; A.F.nrmy = nrmy; A.F.off = off;
+    A.F.M = M; A.F.B = B; A.F.ld = ld; A.F.status = status;
+    A.F.u = p; p += (size_t)(M + 1) * ld;
+    A.F.cx = p; p += (size_t)(M + 3) * ld;
+    A.F.cy = p; p += (size_t)(M + 3) * ld;
+    double* R = p; p += (size_t)N * ld;
+    double* dd = p; p += (size_t)N * ld;
+    double* df = p; p += (size_t)N * ld;
+    A.F.cp = p; p += (size_t)M * ld;
+    A.F.zx = p; p += (size_t)M * ld;
+    A.F.zy = p; p += (size_t)M * ld;
+    A.F.zz = p;
+    A.E = sto::EvalArgs{A.F.u, A.F.cx, A.F.cy, ts, M, N, B, ld, nullptr, nullptr, nullptr, R, dd, df};
+    A.Q.dd = dd; A.Q.df = df; A.Q.R = R; A.Q.sinb = sinb; A.Q.N = N; A.Q.B = B; A.Q.ld = ld;
+    A.Q.v = v; A.Q.a = a; A.Q.tseg = tseg; A.Q.lap = lap; A.Q.status = status;
+    for (int b = 0; b < B; ++b) sto::fast_candidate(A, *V, b, true, 0);
     return 0;
 }
 

@@ -37,7 +37,7 @@ def make_vehicle(scalars, acc_x, acc_c, dcc_x, dcc_c):
 def build():
     srcs = [os.path.join(HERE, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "..", "spline_trajectory_optimization_b200", "csrc", f)
-        for f in ("sto_common.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh")]
+        for f in ("sto_common.cuh", "sto_fast.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-o", LIB, srcs[0]])
     return LIB
@@ -154,3 +154,19 @@ def qss(impl, X, Y, R, sinb, veh, owner=False):
                       None if own is None else own.ctypes.data_as(_ip), _p(lap), _p(summ), st.ctypes.data_as(_ip))
     return dict(v=v.T.copy(), a=a.T.copy(), lat=lat.T.copy(), time=tseg.T.copy(),
                 owner=None if own is None else own.T.copy(), lap=lap, summary=summ.T.copy(), status=st)
+
+
+def fast(cenx, ceny, nrmx, nrmy, sinb, ts, offsets, veh, rounds=2):
+    """Fast mode (sto_fast.cuh) for offsets [B, M].  Returns dict(lap[B], status[B], v, a, time [B, N])."""
+    off = sm(offsets)
+    M, B = off.shape
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    N = len(ts)
+    sb = None if sinb is None else np.ascontiguousarray(sinb, dtype=np.float64)
+    c = [np.ascontiguousarray(x, dtype=np.float64) for x in (cenx, ceny, nrmx, nrmy)]
+    v, a, tseg = (np.empty((N, B)) for _ in range(3))
+    lap = np.empty(B)
+    st = np.zeros(B, dtype=np.int32)
+    lib().hostsim_fast(_p(c[0]), _p(c[1]), _p(c[2]), _p(c[3]), _p(sb), _p(ts), _p(off), M, N, B, B, C.byref(veh),
+                       int(rounds), _p(v), _p(a), _p(tseg), _p(lap), st.ctypes.data_as(_ip))
+    return dict(lap=lap, status=st, v=v.T.copy(), a=a.T.copy(), time=tseg.T.copy())
