@@ -18,6 +18,7 @@
 #include "sto_fit_lsq.cuh"
 #include "sto_qss.cuh"
 #include "sto_qss_memo.cuh"
+#include "sto_qss_memo2.cuh"
 
 namespace {
 
@@ -45,6 +46,8 @@ struct Tuning {
     std::atomic<int> qss_group{0};    // lanes per candidate of the memoised QSS kernel (1, 2, 4, 8, 16, 32)
     std::atomic<int> qss_planes{0};   // 1 = bit planes in shared memory, 2 = global (mixed decided by residency),
                                       // 3 = all global, 4 = CONT planes shared + live / STOP planes global
+    std::atomic<int> qss_kernel{0};   // small batches: 1 = the four-walker kernel (sto_qss_memo.cuh), 2 = the one-loop kernel
+                                      // (sto_qss_memo2.cuh); 0 = the one-loop kernel wherever it applies (N <= 4096)
     std::atomic<int> fit_solver{STO_FIT_FITPACK};   // sto_set_fit_solver
 };
 Tuning g_tune;
@@ -55,6 +58,7 @@ struct TuningFromEnv {
         if (const char* e = getenv("STO_FIT_SOLVER")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.fit_solver = v; }
         if (const char* e = getenv("STO_QSS_LANES")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_lanes = v; }
         if (const char* e = getenv("STO_QSS_GROUP")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_group = v; }
+        if (const char* e = getenv("STO_QSS_KERNEL")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.qss_kernel = v; }
         if (const char* e = getenv("STO_QSS_PLANES"))
             g_tune.qss_planes = (e[0] == 's') ? 1 : (e[0] != 'g') ? 0 : (e[1] == '\0') ? 2 : (e[1] == '0') ? 3 : 4;
     }
@@ -371,6 +375,17 @@ __global__ void fast_kernel(sto::FastArgs Ain, FastTables T, const __grid_consta
     sto::fast_candidate(A, V, active ? t : A.Q.B - 1, active, threadIdx.x & ~31);
 }
 
+// The same launch shape with the one-loop kernel (sto_qss_memo2.cuh): shared evaluate-and-commit, four small search stages.
+template <int G>
+__global__ void qss_memo2_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
+    const int lane = threadIdx.x & 31, warp = blockIdx.x;
+    const int grp = lane / G, g = lane % G;
+    const int b = warp * cpw + grp;
+    const bool active = grp < cpw && b < A.B;
+    const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, nullptr, 0, lane, A.N, W.W);
+    sto::qss_memo2_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G);
+}
+
 // FP64 pipe peak for the roofline report: 8 independent DFMA chains per thread, every SM full.
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = a + threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3, x4 = x0 + 4e-3, x5 = x0 + 5e-3,
@@ -608,6 +623,20 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         while (cpw > 1 && sto::memo_smem_bytes(A.N, cpw) > kMemoSmemBudget) cpw >>= 1;
         const int warps = (A.B + cpw - 1) / cpw;
         const size_t smem = sto::memo_smem_bytes(A.N, cpw);
+        const int which = g_tune.qss_kernel.load();
+        if (which != 1 && w.memo.W <= 64 && G >= 8) {   // the one-loop kernel: lane groups of 8 / 16 / 32, N <= 4096
+#define STO_LAUNCH_MEMO2(GG)                                                                                          \
+    do {                                                                                                              \
+        STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        qss_memo2_kernel<GG><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
+    } while (0)
+            if (G == 32) STO_LAUNCH_MEMO2(32);
+            else if (G == 16) STO_LAUNCH_MEMO2(16);
+            else STO_LAUNCH_MEMO2(8);
+#undef STO_LAUNCH_MEMO2
+            STO_CUDA(cudaGetLastError());
+            return STO_OK;
+        }
 #define STO_LAUNCH_MEMO(GG)                                                                                          \
     do {                                                                                                             \
         STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -648,6 +677,7 @@ int sto_set_tuning(const char* key, int value) {
     if (k == "qss_lanes" && (value == 0 || pow2_le32(value))) { g_tune.qss_lanes = value; return STO_OK; }
     if (k == "qss_group" && (value == 0 || pow2_le32(value))) { g_tune.qss_group = value; return STO_OK; }
     if (k == "qss_planes" && value >= 0 && value <= 4) { g_tune.qss_planes = value; return STO_OK; }
+    if (k == "qss_kernel" && value >= 0 && value <= 2) { g_tune.qss_kernel = value; return STO_OK; }
     return fail(STO_ERR_INVALID, "unknown tuning key or value");
 }
 int sto_fit_solver_lanes(int M, int B) {

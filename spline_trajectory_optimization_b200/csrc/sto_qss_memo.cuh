@@ -161,7 +161,7 @@ STO_HD size_t memo_smem_bytes(int N, int cands) {
     return memo_plane_bytes(N) * (size_t)cands + (size_t)STO_LIST_RING * 32 * sizeof(int32_t);
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // Single-bit atomics on a 64-bit plane word, issued as native 32-bit atomics on the half that holds the bit (a 64-bit
 // atomicAnd / atomicOr on shared memory compiles to a compare-and-swap loop; 7 % of the kernel's stall samples).
 STO_D void atom_set_bit(const Ring& r, int pos) {
@@ -1109,7 +1109,7 @@ STO_HD int memo_spawned_rows_vec(const QssArgs& A, const MemoWork& W, const Memo
     return w;
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // qss_finish for a lane group: one lane walking N records with two divisions per sample was 4.6 % of the kernel
 // (tools/phase_profile.py).  The lanes take samples g, g + G, ... (lateral acceleration, segment time, outputs, extrema -
 // min / max do not depend on the order), park each segment time in the record's radius slot, which nobody reads any

@@ -14,10 +14,10 @@ from spline_trajectory_optimization_b200.evaluator import BatchedLineEvaluator  
 
 lib = _lib.load()
 rt, veh = bench.build_track(), bench.test_vehicle()
-configs = [tuple(int(x) for x in a.split(":")[:2]) + (a.split(":")[2] if a.count(":") > 1 else "s", a.split(":")[3] if a.count(":") > 2 else "4") for a in sys.argv[1:]] or [(4096, 8, 's', '4')]
+configs = [tuple(int(x) for x in a.split(":")[:2]) + (a.split(":")[2] if a.count(":") > 1 else "s", a.split(":")[3] if a.count(":") > 2 else "4", a.split(":")[4] if a.count(":") > 3 else "0") for a in sys.argv[1:]] or [(4096, 8, 's', '4', '0')]
 cache = {}
 ref = None
-for B, lanes, planes, group in configs:
+for B, lanes, planes, group, kern in configs:
     if B not in cache:
         ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), veh, impl="memo")
         off = bench.make_offsets(rt, min(B, 4096), 1234)
@@ -28,6 +28,7 @@ for B, lanes, planes, group in configs:
     _lib.check(lib.sto_set_tuning(b"qss_lanes", int(lanes)))
     _lib.check(lib.sto_set_tuning(b"qss_planes", {"s": 1, "g": 2, "g0": 3, "g1": 4}[planes]))
     _lib.check(lib.sto_set_tuning(b"qss_group", int(group)))
+    _lib.check(lib.sto_set_tuning(b"qss_kernel", int(kern)))
     lib.sto_set_stage_timing(1)
     best = None
     for it in range(3):
@@ -41,6 +42,6 @@ for B, lanes, planes, group in configs:
     if ref is None:
         ref = lap[:4096].copy()
     same = np.array_equal(lap[:min(B, 4096)], ref[:min(B, 4096)])
-    print(f"B={B:7d} lanes={lanes:2d} planes={planes} group={group}  fit {best[1]:8.2f} ms  sample {best[2]:8.2f} ms  qss {best[3]:9.2f} ms  "
+    print(f"B={B:7d} lanes={lanes:2d} planes={planes} group={group} kernel={kern}  fit {best[1]:8.2f} ms  sample {best[2]:8.2f} ms  qss {best[3]:9.2f} ms  "
           f"-> {B / (sum(best) * 1e-3):10.0f} cand/s   laps identical to first config: {same}  status ok: {not st.any().item()}",
           flush=True)
