@@ -376,14 +376,16 @@ __global__ void fast_kernel(sto::FastArgs Ain, FastTables T, const __grid_consta
 }
 
 // The same launch shape with the one-loop kernel (sto_qss_memo2.cuh): shared evaluate-and-commit, four small search stages.
-template <int G>
-__global__ void qss_memo2_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
+// MAXR = register budget per thread: 168 leaves the allocation free (~160 registers, at most 12 one-warp CTAs per SM),
+// 144 / 128 cap it for batches that put 13-14 / more warps on an SM.
+template <int G, int MAXR>
+__global__ void __maxnreg__(MAXR) qss_memo2_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
     const int lane = threadIdx.x & 31, warp = blockIdx.x;
     const int grp = lane / G, g = lane % G;
     const int b = warp * cpw + grp;
     const bool active = grp < cpw && b < A.B;
     const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, nullptr, 0, lane, A.N, W.W);
-    sto::qss_memo2_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G);
+    sto::qss_memo2_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G, grp < cpw ? grp : 0, cpw);
 }
 
 // FP64 pipe peak for the roofline report: 8 independent DFMA chains per thread, every SM full.
@@ -625,14 +627,22 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         const size_t smem = sto::memo_smem_bytes(A.N, cpw);
         const int which = g_tune.qss_kernel.load();
         if (which != 1 && w.memo.W <= 64 && G >= 8) {   // the one-loop kernel: lane groups of 8 / 16 / 32, N <= 4096
-#define STO_LAUNCH_MEMO2(GG)                                                                                          \
-    do {                                                                                                              \
-        STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        qss_memo2_kernel<GG><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
+#define STO_LAUNCH_MEMO2(GG, MB)                                                                                          \
+    do {                                                                                                                  \
+        STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        qss_memo2_kernel<GG, MB><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
     } while (0)
-            if (G == 32) STO_LAUNCH_MEMO2(32);
-            else if (G == 16) STO_LAUNCH_MEMO2(16);
-            else STO_LAUNCH_MEMO2(8);
+#define STO_LAUNCH_MEMO2_G(GG)                                      \
+    do {                                                            \
+        if (per_sm <= 12) STO_LAUNCH_MEMO2(GG, 168);                \
+        else if (per_sm <= 14) STO_LAUNCH_MEMO2(GG, 144);           \
+        else STO_LAUNCH_MEMO2(GG, 128);                             \
+    } while (0)
+            const int per_sm = (warps + 147) / 148;
+            if (G == 32) STO_LAUNCH_MEMO2_G(32);
+            else if (G == 16) STO_LAUNCH_MEMO2_G(16);
+            else STO_LAUNCH_MEMO2_G(8);
+#undef STO_LAUNCH_MEMO2_G
 #undef STO_LAUNCH_MEMO2
             STO_CUDA(cudaGetLastError());
             return STO_OK;

@@ -29,24 +29,82 @@ namespace sto {
 
 #if defined(__CUDACC__)
 
+// Outer iteration 0's dense forward sweep, out of line (it runs once per candidate) and with its in/out scalars passed by
+// value: by reference their address escapes into the call and they would live in local memory for the whole kernel.
+struct Sweep0Out { int nlive, status; long long steps; };
 template <int G>
-__device__ __noinline__ void memo2_sweep0(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                                          int b, double lat0, int& nlive, int64_t& steps, int& status) {
-    memo_forward_sweep0(A, W, C, V, b, lat0, nlive, steps, status);
+__device__ __noinline__ Sweep0Out memo2_sweep0(const QssArgs& A, const MemoWork& W, const MemoCtx& C,
+                                               const sto_vehicle_f64& V, int b, double lat0, int nlive, long long steps,
+                                               int status) {
+    int64_t st = steps;
+    memo_forward_sweep0(A, W, C, V, b, lat0, nlive, st, status);
+    return Sweep0Out{nlive, status, (long long)st};
 }
+
+// The six bit planes of one candidate, addressed through the dynamic shared-memory array itself so that every access is
+// an LDS / STS / ATOMS with 32-bit address arithmetic (through MemoCtx's generic pointers they were generic LD / ST with
+// 64-bit address chains: 22 % of the kernel's instructions were IMADs).  Same layout as memo_bind: plane k = 2 * kind +
+// direction (kind 0 live, 1 CONT, 2 STOP), word w of candidate column `col` at [(k * NW + w) * cpw + col].
+extern __shared__ unsigned long long sto_memo2_planes[];
+struct SPlanes {
+    int col, cpw, NW, N;
+    __device__ __forceinline__ u64& at(int k, int w) const { return sto_memo2_planes[(k * NW + w) * cpw + col]; }
+    __device__ __forceinline__ u64 word(int k, int w) const { return at(k, w); }
+    __device__ __forceinline__ void set_word(int k, int w, u64 x) const { at(k, w) = x; }
+    __device__ __forceinline__ bool test(int k, int p) const { return (at(k, p >> 6) >> (p & 63)) & 1ull; }
+    __device__ __forceinline__ void atom_set(int k, int pos) const {
+        atomicOr(reinterpret_cast<unsigned*>(&at(k, pos >> 6)) + ((pos >> 5) & 1), 1u << (pos & 31));
+    }
+    __device__ __forceinline__ void atom_clear(int k, int pos) const {
+        atomicAnd(reinterpret_cast<unsigned*>(&at(k, pos >> 6)) + ((pos >> 5) & 1), ~(1u << (pos & 31)));
+    }
+    // 64 bits starting at bit `pos` (no ring wrap; bits past the last word read as 0)
+    __device__ __forceinline__ u64 read64(int k, int pos) const {
+        const int w = pos >> 6, sh = pos & 63;
+        u64 x = at(k, w) >> sh;
+        if (sh && w + 1 < NW) x |= at(k, w + 1) << (64 - sh);
+        return x;
+    }
+    // bit t of the result = ring position (start + t) mod N, t = 0..63; needs N >= 64, 0 <= start < N
+    __device__ __forceinline__ u64 window(int k, int start) const {
+        const int avail = N - start;
+        u64 lo = read64(k, start);
+        if (avail >= 64) return lo;
+        lo &= (1ull << avail) - 1ull;
+        return lo | (read64(k, 0) << avail);
+    }
+};
+enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5 };
+
+#if defined(STO_PHASE_CLOCKS)
+#define STO2_CLK(slot) { const long long c_ = clock64(); clk2[slot] += c_ - t2; t2 = c_; }
+#define STO2_CNT(slot) { clk2[slot] += 1; }
+#else
+#define STO2_CLK(slot)
+#define STO2_CNT(slot)
+#endif
 
 template <int G>
 __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
-                                    int b, bool active, int g, int lane0) {
+                                    int b, bool active, int g, int lane0, int col, int cpw) {
     const int N = A.N, ld = A.ld, NW = W.W;
+    const SPlanes P{col, cpw, NW, N};
     const unsigned full = 0xffffffffu;
     const unsigned gbits = (G == 32) ? full : ((1u << G) - 1u);
     const double lat0 = max_lat_acc(V, 0.0);
     double* rec = A.rec + (size_t)b * N * 4;
     int32_t* LB = W.spB + (size_t)b * A.cap;   // candidate-major lists of virtual rows (creation order)
     int32_t* LF = W.spF + (size_t)b * A.cap;
-    const Ring live0 = C.live(0), live1 = C.live(1), cont0 = C.cont(0), cont1 = C.cont(1), stop0 = C.stop(0), stop1 = C.stop(1);
+    __builtin_assume(__isGlobal(rec));
+    __builtin_assume(__isGlobal(LB));
+    __builtin_assume(__isGlobal(LF));
     int status = 0;
+#if defined(STO_PHASE_CLOCKS)
+    // profiling build (tools/phase_profile.py): [4 * k + phase], k = 0 search clocks, 1 evaluate clocks, 2 commit + post
+    // clocks, 3 evaluation rounds of the warp
+    long long clk2[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t2 = clock64();
+#endif
     if (active) {
         for (int i = g; i < N; i += G) {  // simulator.py:133-147; sample-major inputs -> this candidate's records
             const double Ri = A.R[at(i, ld, b)];
@@ -58,9 +116,9 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
         for (int w = g; w < NW; w += G) {
             const int nb = N - 64 * w;
             const u64 ones = (nb >= 64) ? ~0ull : ((1ull << nb) - 1ull);
-            live0.set_word(w, ones); live1.set_word(w, ones);
-            cont0.set_word(w, 0); cont1.set_word(w, 0);
-            stop0.set_word(w, 0); stop1.set_word(w, 0);
+            P.set_word(PL_LIVE0, w, ones); P.set_word(PL_LIVE1, w, ones);
+            P.set_word(PL_CONT0, w, 0); P.set_word(PL_CONT1, w, 0);
+            P.set_word(PL_STOP0, w, 0); P.set_word(PL_STOP1, w, 0);
         }
     }
     __syncwarp();
@@ -95,7 +153,10 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     chunk = (g < nlist) ? list[g] : -1;
                     nchunk = (G + g < nlist) ? list[G + g] : -1;
                 } else if (phase == 2) {
-                    if (iters == 0 && !done && nliveF == N) memo2_sweep0<G>(A, W, C, V, b, lat0, nliveF, steps, status);
+                    if (iters == 0 && !done && nliveF == N) {
+                        const Sweep0Out o = memo2_sweep0<G>(A, W, C, V, b, lat0, nliveF, steps, status);
+                        nliveF = o.nlive; status = o.status; steps = o.steps;
+                    }
                     skip = done || nliveF == 0;
                     todo = wordsF; open = false;
                 } else {
@@ -107,6 +168,9 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 }
             }
             const bool fwd = phase >= 2;
+#if defined(STO_PHASE_CLOCKS)
+            t2 = clock64();
+#endif
             // ---- search: the front(s) of this candidate that need an evaluation now
             bool has = false, kill = false, committer = false;
             int p = 0, slot = 0, nb_batch = 0;
@@ -118,12 +182,12 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                             if (!todo) break;
                             w = ctz64(todo);
                             todo &= todo - 1ull;
-                            L = live0.word(w);
+                            L = P.word(PL_LIVE0, w);
                             if (!L) { wordsB &= ~(1ull << w); continue; }
                             steps += popc64(L);
                             int start = 64 * w - s;
                             if (start < 0) start += N;
-                            att = L & ~cont0.window(start);
+                            att = L & ~P.window(PL_CONT0, start);
                             open = true;
                         }
                         if (!att) {
@@ -142,7 +206,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         p = 64 * w + slot - s;
                         if (p < 0) p += N;
                         has = true;
-                        kill = stop0.test(p);
+                        kill = P.test(PL_STOP0, p);
                     }
                 }
                 committer = has;
@@ -177,7 +241,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         if (conflict) { held = iv; closed = true; }
                         else {
                             ++steps;
-                            const bool c0 = cont0.test(pp), s0 = stop0.test(pp);
+                            const bool c0 = P.test(PL_CONT0, pp), s0 = P.test(PL_STOP0, pp);
                             if (c0) { if (wr != r - 1 && g == 0) list[wr] = iv; ++wr; }
                             else if (!s0) {
                                 if (g == cnt) { my_p = pp; my_slot = wr; }
@@ -200,16 +264,16 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                             if (!todo) break;
                             w = ctz64(todo);
                             todo &= todo - 1ull;
-                            L = live1.word(w);
+                            L = P.word(PL_LIVE1, w);
                             if (!L) { wordsF &= ~(1ull << w); continue; }
                             steps += popc64(L);
                             int start = 64 * w + s;
                             if (start >= N) start -= N;
-                            att = L & ~cont1.window(start);
+                            att = L & ~P.window(PL_CONT1, start);
                             open = true;
                         }
                         if (!att) {
-                            live1.set_word(w, L);
+                            P.set_word(PL_LIVE1, w, L);
                             if (!L) wordsF &= ~(1ull << w);
                             open = false;
                             continue;
@@ -218,7 +282,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         bit = 1ull << t;
                         p = 64 * w + t + s;
                         if (p >= N) p -= N;
-                        if (stop1.test(p)) { L &= ~bit; --nliveF; att &= ~bit; continue; }
+                        if (P.test(PL_STOP1, p)) { L &= ~bit; --nliveF; att &= ~bit; continue; }
                         has = true;
                         break;
                     }
@@ -233,7 +297,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     const bool valid = searching && mine < nlist;
                     int pp = valid ? cur + s : 0;
                     if (pp >= N) pp -= N;
-                    const bool c0 = cont1.test(pp), s0 = stop1.test(pp);
+                    const bool c0 = P.test(PL_CONT1, pp), s0 = P.test(PL_STOP1, pp);
                     const bool c = valid && c0;
                     const bool pe = valid && !c0 && !s0;
                     const int rot = r & (G - 1);
@@ -272,6 +336,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 }
                 committer = has && g == 0;
             }
+            STO2_CLK(phase)
             if (!warp_any(has)) {
                 // ---- phase over for every candidate of the warp
                 if (phase == 1) wB = wr;
@@ -291,6 +356,8 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 else res = eval_pure(A, V, b, fwd, p, q, lat0);
             }
             __syncwarp();
+            STO2_CLK(4 + phase)
+            STO2_CNT(12 + phase)
             // ---- commit, all lanes at once.  Sequentially (row / list order) front k would: clear the memos around q_k,
             // then set its own edge's memo at p_k.  Inside one batch the only interaction is that the NEXT front, if adjacent
             // and state-changing, clears the bit front k just set (its q is p_k).  So: phase 1 = state write + own-edge memo,
@@ -299,30 +366,31 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                                          res.kind == EV_RESPAWN || res.kind == EV_ZERO);
             const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
             const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
-            const Ring co = fwd ? cont1 : cont0, so = fwd ? stop1 : stop0;
+            const int co = PL_CONT0 + d, so = PL_STOP0 + d;
             if (committer) {
                 if (changed) {
                     double* rq = rec + 4 * (size_t)q;
                     rq[0] = res.v_new;
                     rq[1] = res.a_new;
                 }
-                if (res.kind == EV_WRITE || res.kind == EV_KEEP) { atom_set_bit(co, p); atom_clear_bit(so, p); }
-                else if (res.kind == EV_STOP) { atom_set_bit(so, p); atom_clear_bit(co, p); }
-                else if (res.kind == EV_SPAWN) { atom_clear_bit(co, p); atom_clear_bit(so, p); }
+                if (res.kind == EV_WRITE || res.kind == EV_KEEP) { P.atom_set(co, p); P.atom_clear(so, p); }
+                else if (res.kind == EV_STOP) { P.atom_set(so, p); P.atom_clear(co, p); }
+                else if (res.kind == EV_SPAWN) { P.atom_clear(co, p); P.atom_clear(so, p); }
                 if (stopped) {
-                    if (phase == 0) atom_clear_bit(live0, 64 * w + slot);
+                    if (phase == 0) P.atom_clear(PL_LIVE0, 64 * w + slot);
                     else if (phase == 1) list[slot] = -1;        // tombstone: the next walk drops it
                 }
             }
             __syncwarp();
             if (committer && changed) {   // memo_invalidate(q) minus this front's own edge (bit p of its own direction)
                 const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
-                atom_clear_bit(cont0, q);                                             // edge q -> q-1
-                atom_clear_bit(stop0, q);
-                atom_clear_bit(cont1, q);                                             // edge q -> q+1
-                atom_clear_bit(stop1, q);
-                if (fwd) { atom_clear_bit(cont0, qn); atom_clear_bit(stop0, qn); }    // edge q+1 -> q   (own: q-1 -> q)
-                else { atom_clear_bit(cont1, qp); atom_clear_bit(stop1, qp); }        // edge q-1 -> q   (own: q+1 -> q)
+                P.atom_clear(PL_CONT0, q);                                            // edge q -> q-1
+                P.atom_clear(PL_STOP0, q);
+                P.atom_clear(PL_CONT1, q);                                            // edge q -> q+1
+                P.atom_clear(PL_STOP1, q);
+                const int e2 = fwd ? qn : qp;      // forward: edge q+1 -> q (own: q-1 -> q); backward: edge q-1 -> q (own: q+1 -> q)
+                P.atom_clear(fwd ? PL_CONT0 : PL_CONT1, e2);
+                P.atom_clear(fwd ? PL_STOP0 : PL_STOP1, e2);
             }
             // ---- bookkeeping, mirrored on every lane of the group
             const unsigned stop_b = (__ballot_sync(full, stopped && committer) >> lane0) & gbits;
@@ -344,7 +412,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             if (phase == 0) {
                 nliveB -= __popc(stop_b);
                 if (nb_batch) {
-                    L = live0.word(w);
+                    L = P.word(PL_LIVE0, w);
                     att &= ~lowest_bits(att, nb_batch);
                 }
             } else if (phase == 1) {
@@ -363,6 +431,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     ++wr;
                 }
             }
+            STO2_CLK(8 + phase)
         }
         __syncwarp();   // list entries stored by one lane are read by another in the fold / the next walk
         if (!done && wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
@@ -394,6 +463,10 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
         }
     }
     qss_finish_group<G>(A, rec, b, active, status, steps, iters, g, lane0);
+#if defined(STO_PHASE_CLOCKS)
+    if (active && g == 0 && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)clk2[k];
+    if (active && g == 0 && A.lat) for (int k = 0; k < 8; ++k) A.lat[at(k, ld, b)] = (double)clk2[8 + k];
+#endif
 }
 
 #endif  // __CUDACC__

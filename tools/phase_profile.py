@@ -37,14 +37,25 @@ for _ in range(2):
     torch.cuda.synchronize()
     print("qss ms (incl. chord kernel)", e0.elapsed_time(e1))
 summ = res["summary"][:, :B].cpu().numpy()
-names = ["loop head", "orig backward", "spawned backward", "orig forward", "spawned forward", "compaction",
-         "loop tail", "finish"]
-tot = summ.sum(axis=0)
-print("per-thread total clocks: mean %.3g  (%.1f ms at 1.965 GHz)" % (tot.mean(), tot.mean() / 1.965e6))
-for k, n in enumerate(names):
-    print("%-18s %6.2f %%   mean clocks %.3g" % (n, 100 * summ[k].mean() / tot.mean(), summ[k].mean()))
 sub = res["lat_acc"][:8, :B].cpu().numpy()
-subn = ["orig search clk", "orig eval clk", "spawned search clk", "spawned eval clk", "orig evals (lane)", "spawned evals (lane)",
-        "spawned warp rounds", "orig warp rounds"]
-for k, n in enumerate(subn):
-    print("%-22s mean %.4g   max %.4g" % (n, sub[k].mean(), sub[k].max()))
+if int(os.environ.get("STO_QSS_KERNEL", "0")) == 1:
+    names = ["loop head", "orig backward", "spawned backward", "orig forward", "spawned forward", "compaction",
+             "loop tail", "finish"]
+    tot = summ.sum(axis=0)
+    print("per-thread total clocks: mean %.3g  (%.1f ms at 1.965 GHz)" % (tot.mean(), tot.mean() / 1.965e6))
+    for k, n in enumerate(names):
+        print("%-18s %6.2f %%   mean clocks %.3g" % (n, 100 * summ[k].mean() / tot.mean(), summ[k].mean()))
+    subn = ["orig search clk", "orig eval clk", "spawned search clk", "spawned eval clk", "orig evals (lane)", "spawned evals (lane)",
+            "spawned warp rounds", "orig warp rounds"]
+    for k, n in enumerate(subn):
+        print("%-22s mean %.4g   max %.4g" % (n, sub[k].mean(), sub[k].max()))
+else:
+    # one-loop kernel (sto_qss_memo2.cuh): [4 k + phase], k = 0 search, 1 evaluate, 2 commit + post clocks, 3 warp rounds
+    allv = np.concatenate([summ, sub], axis=0)
+    ph = ["bwd original rows", "bwd re-spawned list", "fwd original rows", "fwd re-spawned list"]
+    tot = allv[:12].sum(axis=0).mean()
+    print("clocks inside the round loop per candidate: mean %.3g (%.1f ms at 1.965 GHz)" % (tot, tot / 1.965e6))
+    for p_ in range(4):
+        se, ev, co, rd = (allv[4 * k + p_].mean() for k in range(4))
+        print("%-20s search %5.1f %%  evaluate %5.1f %%  commit+post %5.1f %%   rounds %7.0f   clocks/round: search %6.0f eval %6.0f commit %6.0f"
+              % (ph[p_], 100 * se / tot, 100 * ev / tot, 100 * co / tot, rd, se / max(rd, 1), ev / max(rd, 1), co / max(rd, 1)))
