@@ -377,7 +377,7 @@ __global__ void fast_kernel(sto::FastArgs Ain, FastTables T, const __grid_consta
 
 // The same launch shape with the one-loop kernel (sto_qss_memo2.cuh): shared evaluate-and-commit, four small search stages.
 // MAXR = register budget per thread: 168 leaves the allocation free (~160 registers, at most 12 one-warp CTAs per SM),
-// 144 / 128 cap it for batches that put 13-14 / more warps on an SM.
+// 144 / 128 cap it for batches that put 13 / more warps on an SM.
 template <int G, int MAXR>
 __global__ void __maxnreg__(MAXR) qss_memo2_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
     const int lane = threadIdx.x & 31, warp = blockIdx.x;
@@ -635,7 +635,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
 #define STO_LAUNCH_MEMO2_G(GG)                                      \
     do {                                                            \
         if (per_sm <= 12) STO_LAUNCH_MEMO2(GG, 168);                \
-        else if (per_sm <= 14) STO_LAUNCH_MEMO2(GG, 144);           \
+        else if (per_sm <= 13) STO_LAUNCH_MEMO2(GG, 144);           \
         else STO_LAUNCH_MEMO2(GG, 128);                             \
     } while (0)
             const int per_sm = (warps + 147) / 148;

@@ -76,6 +76,68 @@ struct SPlanes {
 };
 enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5 };
 
+// The front step with its independent sub-chains free to overlap.  eval_core (sto_qss_memo.cuh) is three divisions and
+// five square roots that nvcc expands into fast path + guarded call to a slow path each: no two of them overlap in one
+// warp, ~1,500 cycles of dependent latency per evaluation on the critical path of every round.  Here the SAME operations
+// in the SAME order per value (every result is bit-identical) are written with the flagged branch-free division / square
+// root of sto_common.cuh (identical bits while the operand-range flag is down; sto_selftest_fp64), so the compiler sees one
+// basic block in which  dd / v -> jerk window -> state speeds,  friction ellipse -> curve speed,  the two table look-ups
+// and the re-initialisation speed  run side by side (~500 cycles of dependent latency).  Anything unusual - a raised flag
+// (zero / infinite / denormal / NaN operand), v_p == 0 - is redone out of line with the plain operators.
+__device__ __noinline__ EvalRes eval_core_plain(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
+                                                double aq_old, double dd, double Rq, double gq, double lat0) {
+    return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+}
+__device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
+                                                 double aq_old, double dd, double Rq, double gq, double lat0) {
+    bool slow = false;
+    const double dt = div_fast(dd, vp, slow);                                     // front_step_rt: dt = dd / vp
+    const double l = np_clip(ap, V.max_lon_dcc, V.max_lon_acc);                   // max_lat_acc(V, ap)
+    const double Lx = (l > 0.0) ? V.max_lon_acc : V.max_lon_dcc;
+    const double ell = V.max_left_acc * sqrt_fast(1.0 - div_fast(l * l, Lx * Lx, slow), slow);
+    const double mc = sqrt_fast(fabs(fabs(ell) - gq) * Rq, slow);                 // calc_v(max_lat_acc, Rq, gq)
+    const double vinit = sqrt_fast(fabs(fabs(lat0) - gq) * Rq, slow);             // init_speed's calc_v (used on a re-spawn)
+    const double vacc = ppoly4(V.acc_x, V.acc_c, V.n_acc, vp);
+    const double vdcc = ppoly4(V.dcc_x, V.dcc_c, V.n_dcc, vp);
+    const double md = dt * V.max_jerk;
+    double hi = ap + md, lo = ap - md;
+    hi = np_clip(hi, vdcc, vacc);
+    lo = np_clip(lo, vdcc, vacc);
+    const double vp2 = vp * vp;
+    const double th = 2 * hi * dd, tl = 2 * lo * dd;
+    const double s_hi = sqrt_fast(py_max(fwd ? th + vp2 : vp2 - th, 0.0), slow);
+    const double s_lo = sqrt_fast(py_max(fwd ? tl + vp2 : vp2 - tl, 0.0), slow);
+    const double smax = fwd ? s_hi : s_lo, smin = fwd ? s_lo : s_hi;
+    const double g = py_min3(smax, mc, V.max_speed);
+    const bool respawn = (g > mc) || (g < smin);
+    const bool valid = smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
+    const double gg = g * g;
+    const double aq = div_fast(fwd ? gg - vp2 : vp2 - gg, 2 * dd, slow);
+    if (slow || vp == 0.0) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+    EvalRes r;
+    r.v_new = 0.0; r.a_new = 0.0;
+    if (valid) {
+        if (vq < g) { r.kind = EV_STOP; return r; }
+        r.v_new = g; r.a_new = aq;
+        r.kind = (!same_bits(vq, g) || !same_bits(aq_old, aq)) ? EV_WRITE : EV_KEEP;
+        return r;
+    }
+    if (fwd || !respawn) { r.kind = EV_STOP; return r; }
+    const double vi = (V.max_speed < vinit) ? V.max_speed : vinit;
+    r.v_new = vi;
+    r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;
+    return r;
+}
+__device__ __forceinline__ EvalRes eval_pure_ilp(const QssArgs& A, const sto_vehicle_f64& V, const double* rec, bool fwd,
+                                                 int p, int q, double lat0) {
+    const double* rp = rec + 4 * (size_t)p;     // both 32-byte records are fetched up front: one overlapped round trip
+    const double* rq = rec + 4 * (size_t)q;
+    const double vp = rp[0], ap = rp[1], ddp = rp[2];
+    const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
+    const double dd = fwd ? ddp : ddq;          // the chord between p and q is stored at the lower sample
+    return eval_core_ilp(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);
+}
+
 #if defined(STO_PHASE_CLOCKS)
 #define STO2_CLK(slot) { const long long c_ = clock64(); clk2[slot] += c_ - t2; t2 = c_; }
 #define STO2_CNT(slot) { clk2[slot] += 1; }
@@ -353,7 +415,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             res.kind = EV_NONE; res.v_new = 0.0; res.a_new = 0.0;
             if (has) {
                 if (kill) res.kind = EV_KILL;
-                else res = eval_pure(A, V, b, fwd, p, q, lat0);
+                else res = eval_pure_ilp(A, V, rec, fwd, p, q, lat0);
             }
             __syncwarp();
             STO2_CLK(4 + phase)
