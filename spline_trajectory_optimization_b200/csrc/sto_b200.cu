@@ -56,7 +56,7 @@ struct TuningFromEnv {
     TuningFromEnv() {
         if (const char* e = getenv("STO_FIT_SPLIT")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.fit_split = v; }
         if (const char* e = getenv("STO_FIT_SOLVER")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.fit_solver = v; }
-        if (const char* e = getenv("STO_QSS_LANES")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_lanes = v; }
+        if (const char* e = getenv("STO_QSS_LANES")) { const int v = atoi(e); if (v >= 1 && v <= 32) g_tune.qss_lanes = v; }
         if (const char* e = getenv("STO_QSS_GROUP")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_group = v; }
         if (const char* e = getenv("STO_QSS_KERNEL")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.qss_kernel = v; }
         if (const char* e = getenv("STO_QSS_PLANES"))
@@ -618,6 +618,14 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         // measured on B200 (Monza, 4,096 candidates): 4 candidates x 8 lanes per warp 63.3 ms, 8 x 4 lanes 65.1 ms,
         // 8 x 2 lanes 72.9 ms; larger batches fill the SMs with 8 candidates per warp
         int G = ((A.B + 3) / 4 <= 148 * 8) ? 8 : 4;
+        // the one-loop kernel (N <= 4096) measured on B200, Monza: 1,024 candidates 28.5 ms at 1 x 32 lanes per warp vs 32.8
+        // at 2 x 16; 2,048: 35.2 ms at 2 x 16 vs 43.8 at 4 x 8; 4,096: 41.0 ms at 2 x 16 vs 43.1 at 4 x 8 (and 62 at 1 x 32);
+        // 8,192: 49.6 ms at 4 x 8 (2 x 16 would put 28 warps on an SM)
+        if (g_tune.qss_kernel.load() != 1 && w.memo.W <= 64) {
+            if (A.B <= 148 * 8) G = 32;
+            else if ((A.B + 1) / 2 <= 148 * 14) G = 16;
+            else G = 8;
+        }
         if (const int v = g_tune.qss_group.load()) G = v;
         const size_t per_cand = sto::memo_plane_bytes(A.N);
         int cpw = pick_lanes(A.B, per_cand);
@@ -684,7 +692,7 @@ int sto_set_tuning(const char* key, int value) {
     if (!key) return fail(STO_ERR_INVALID, "key is NULL");
     const std::string k(key);
     if (k == "fit_split" && (value == 0 || pow2_le32(value))) { g_tune.fit_split = value; return STO_OK; }
-    if (k == "qss_lanes" && (value == 0 || pow2_le32(value))) { g_tune.qss_lanes = value; return STO_OK; }
+    if (k == "qss_lanes" && value >= 0 && value <= 32) { g_tune.qss_lanes = value; return STO_OK; }
     if (k == "qss_group" && (value == 0 || pow2_le32(value))) { g_tune.qss_group = value; return STO_OK; }
     if (k == "qss_planes" && value >= 0 && value <= 4) { g_tune.qss_planes = value; return STO_OK; }
     if (k == "qss_kernel" && value >= 0 && value <= 2) { g_tune.qss_kernel = value; return STO_OK; }

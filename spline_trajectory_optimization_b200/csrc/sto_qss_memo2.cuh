@@ -29,18 +29,6 @@ namespace sto {
 
 #if defined(__CUDACC__)
 
-// Outer iteration 0's dense forward sweep, out of line (it runs once per candidate) and with its in/out scalars passed by
-// value: by reference their address escapes into the call and they would live in local memory for the whole kernel.
-struct Sweep0Out { int nlive, status; long long steps; };
-template <int G>
-__device__ __noinline__ Sweep0Out memo2_sweep0(const QssArgs& A, const MemoWork& W, const MemoCtx& C,
-                                               const sto_vehicle_f64& V, int b, double lat0, int nlive, long long steps,
-                                               int status) {
-    int64_t st = steps;
-    memo_forward_sweep0(A, W, C, V, b, lat0, nlive, st, status);
-    return Sweep0Out{nlive, status, (long long)st};
-}
-
 // The six bit planes of one candidate, addressed through the dynamic shared-memory array itself so that every access is
 // an LDS / STS / ATOMS with 32-bit address arithmetic (through MemoCtx's generic pointers they were generic LD / ST with
 // 64-bit address chains: 22 % of the kernel's instructions were IMADs).  Same layout as memo_bind: plane k = 2 * kind +
@@ -138,6 +126,100 @@ __device__ __forceinline__ EvalRes eval_pure_ilp(const QssArgs& A, const sto_veh
     return eval_core_ilp(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);
 }
 
+// Outer iteration 0's dense forward sweep (memo_forward_sweep0 of sto_qss_memo.cuh: rows 0 .. N-2 in row order, source
+// state carried in registers, the target record requested one row ahead, plane bits collected per 64-row word) on the
+// shared-array planes and with the overlapped evaluation.  Out of line - it runs once per candidate - and with its in / out
+// scalars by value: by reference their address escapes into the call and they would live in local memory for the whole
+// kernel.
+struct Sweep0Out { int nlive, status; long long steps; };
+__device__ __noinline__ Sweep0Out memo2_sweep0(const QssArgs& A, const sto_vehicle_f64& V, double* rec, SPlanes P,
+                                               double lat0, int nlive, long long steps, int status) {
+    const int N = P.N, NW = P.NW;
+    double vp = rec[0], ap = rec[1], ddp = rec[2];
+    double nv = rec[4], na = rec[5], nd = rec[6], nR = rec[7];   // record of sample 1, then always one row ahead
+    u64 clr = 0, clr_next = 0;   // backward memo bits to forget: this word, the next one
+    bool wrap0 = false;
+    for (int w = 0; w < NW; ++w) {
+        const int i0 = 64 * w;
+        const int n = (N - 1 - i0 < 64) ? (N - 1 - i0) : 64;   // rows i0 .. i0+n-1 (all <= N-2)
+        u64 contw = 0, stopw = 0;
+        for (int t = 0; t < n; ++t) {
+            const int q = i0 + t + 1;
+            const double vq = nv, aq_old = na, ddq = nd, Rq = nR;
+            if (q + 1 < N) {
+                const double* rn = rec + 4 * (size_t)(q + 1);
+                nv = rn[0]; na = rn[1]; nd = rn[2]; nR = rn[3];
+            }
+            const EvalRes r = eval_core_ilp(V, true, vp, ap, vq, aq_old, ddp, Rq, gsb_at(A, q), lat0);
+            if (r.kind == EV_WRITE || r.kind == EV_KEEP) {
+                contw |= 1ull << t;
+                if (r.kind == EV_WRITE) {
+                    rec[4 * (size_t)q + 0] = r.v_new;
+                    rec[4 * (size_t)q + 1] = r.a_new;
+                    const int bq = t + 1, b1 = t + 2;              // bits of q and q + 1 relative to this word
+                    if (bq < 64) clr |= 1ull << bq; else clr_next |= 1ull << (bq - 64);
+                    if (q + 1 == N) wrap0 = true;
+                    else if (b1 < 64) clr |= 1ull << b1;
+                    else clr_next |= 1ull << (b1 - 64);
+                }
+                vp = r.v_new; ap = r.a_new;                        // KEEP: bit-identical to what q holds
+            } else {                                               // EV_STOP, or EV_ZERO (the reference raises)
+                if (r.kind == EV_ZERO) status |= STO_CAND_ZERO_SPEED; else stopw |= 1ull << t;
+                --nlive;
+                ++steps;                                           // (the fronts that go on are counted by the general walk)
+                vp = vq; ap = aq_old;
+            }
+            ddp = ddq;
+        }
+        if (n > 0) {
+            const u64 m = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+            P.set_word(PL_LIVE1, w, (P.word(PL_LIVE1, w) & ~m) | contw);
+            P.set_word(PL_CONT1, w, (P.word(PL_CONT1, w) & ~m) | contw);
+            P.set_word(PL_STOP1, w, (P.word(PL_STOP1, w) & ~m) | stopw);
+        }
+        if (clr) { P.set_word(PL_CONT0, w, P.word(PL_CONT0, w) & ~clr); P.set_word(PL_STOP0, w, P.word(PL_STOP0, w) & ~clr); }
+        clr = clr_next;
+        clr_next = 0;
+    }
+    if (wrap0) { P.set_word(PL_CONT0, 0, P.word(PL_CONT0, 0) & ~1ull); P.set_word(PL_STOP0, 0, P.word(PL_STOP0, 0) & ~1ull); }
+    return Sweep0Out{nlive, status, steps};
+}
+
+// Which 64-row words of a sub-pass over the original rows hold a front that needs attention (a live front whose edge is
+// not known-clean)?  The serial walk paid ~150 cycles for every live word - 46 words per sub-pass, nearly all of them
+// clean - and the candidates of a warp diverged in it.  Here the G lanes of the group take the words g, g + G, ... and
+// test them side by side (a few LDS and shifts each, the same instruction stream for every lane of the warp); the
+// group then ORs its findings.  Returns the mask of words to visit; adds the live fronts to `steps` (every live front
+// takes a step in the reference's schedule), drops words without live fronts from `words`.
+template <int G>
+__device__ __forceinline__ u64 memo2_scan_words(const SPlanes& P, bool fwd, bool skip, int s, int g, u64& words,
+                                                int64_t& steps) {
+    const unsigned full = 0xffffffffu;
+    const int plL = fwd ? PL_LIVE1 : PL_LIVE0, plC = fwd ? PL_CONT1 : PL_CONT0;
+    const u64 t = skip ? 0ull : words;
+    u64 need = 0, dead = 0;
+    int cnt = 0;
+    for (int w0 = g; w0 < P.NW; w0 += G) {
+        if (!((t >> w0) & 1ull)) continue;
+        const u64 Lw = P.word(plL, w0);
+        if (!Lw) { dead |= 1ull << w0; continue; }
+        cnt += popc64(Lw);
+        int start = fwd ? 64 * w0 + s : 64 * w0 - s;
+        if (start >= P.N) start -= P.N;
+        if (start < 0) start += P.N;
+        if (Lw & ~P.window(plC, start)) need |= 1ull << w0;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        need |= __shfl_xor_sync(full, need, o);
+        dead |= __shfl_xor_sync(full, dead, o);
+        cnt += __shfl_xor_sync(full, cnt, o);
+    }
+    steps += cnt;
+    words &= ~dead;
+    return need;
+}
+
 #if defined(STO_PHASE_CLOCKS)
 #define STO2_CLK(slot) { const long long c_ = clock64(); clk2[slot] += c_ - t2; t2 = c_; }
 #define STO2_CNT(slot) { clk2[slot] += 1; }
@@ -208,7 +290,8 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 entering = false;
                 if (phase == 0) {
                     skip = done || nliveB == 0;
-                    todo = wordsB; open = false;
+                    todo = memo2_scan_words<G>(P, false, skip, s, g, wordsB, steps);
+                    open = false;
                 } else if (phase == 1) {
                     if (!warp_any(!done && nB > 0)) { phase = 2; entering = true; continue; }
                     list = LB; nlist = done ? 0 : nB; r = 0; wr = 0; held = -2;
@@ -216,11 +299,12 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     nchunk = (G + g < nlist) ? list[G + g] : -1;
                 } else if (phase == 2) {
                     if (iters == 0 && !done && nliveF == N) {
-                        const Sweep0Out o = memo2_sweep0<G>(A, W, C, V, b, lat0, nliveF, steps, status);
+                        const Sweep0Out o = memo2_sweep0(A, V, rec, P, lat0, nliveF, steps, status);
                         nliveF = o.nlive; status = o.status; steps = o.steps;
                     }
                     skip = done || nliveF == 0;
-                    todo = wordsF; open = false;
+                    todo = memo2_scan_words<G>(P, true, skip, s, g, wordsF, steps);
+                    open = false;
                 } else {
                     if (!warp_any(!done && nF > 0)) break;
                     list = LF; nlist = done ? 0 : nF; r = 0; wr = 0;
@@ -245,8 +329,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                             w = ctz64(todo);
                             todo &= todo - 1ull;
                             L = P.word(PL_LIVE0, w);
-                            if (!L) { wordsB &= ~(1ull << w); continue; }
-                            steps += popc64(L);
+                            if (!L) continue;
                             int start = 64 * w - s;
                             if (start < 0) start += N;
                             att = L & ~P.window(PL_CONT0, start);
@@ -327,8 +410,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                             w = ctz64(todo);
                             todo &= todo - 1ull;
                             L = P.word(PL_LIVE1, w);
-                            if (!L) { wordsF &= ~(1ull << w); continue; }
-                            steps += popc64(L);
+                            if (!L) continue;
                             int start = 64 * w + s;
                             if (start >= N) start -= N;
                             att = L & ~P.window(PL_CONT1, start);
@@ -443,7 +525,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     else if (phase == 1) list[slot] = -1;        // tombstone: the next walk drops it
                 }
             }
-            __syncwarp();
+            if (phase < 2) __syncwarp();   // single phases: one committing lane per group, its atomics stay in program order
             if (committer && changed) {   // memo_invalidate(q) minus this front's own edge (bit p of its own direction)
                 const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
                 P.atom_clear(PL_CONT0, q);                                            // edge q -> q-1
@@ -474,8 +556,12 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             if (phase == 0) {
                 nliveB -= __popc(stop_b);
                 if (nb_batch) {
+                    const bool row0 = (att & 1ull) != 0;     // lane 0's member is row 0 (bit 0 of word 0)
                     L = P.word(PL_LIVE0, w);
                     att &= ~lowest_bits(att, nb_batch);
+                    // the seam: row 0 wrote the sample row N-1 reads in this very sub-pass -> the last word is (re)visited,
+                    // its attention mask formed when the walk gets there
+                    if (w == 0 && (chg_b & 1u) && row0) todo |= 1ull << (NW - 1);
                 }
             } else if (phase == 1) {
                 if (status != 0) { nlist = r; held = -2; }   // abandon the walk of a failed candidate
@@ -485,7 +571,10 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     if (stop_b) { L &= ~bit; --nliveF; }
                     // the next row reads the sample just written: it faces a dirty edge now if it is live (bit t + 1; row 63's
                     // successor belongs to the next word, whose window is formed when the walk gets there)
-                    if (chg_b) att |= L & (bit << 1);
+                    if (chg_b) {
+                        att |= L & (bit << 1);
+                        if ((bit >> 63) && w + 1 < NW) todo |= 1ull << (w + 1);   // row 63's successor opens the next word
+                    }
                 }
             } else {
                 if (has && !stop_b) {
