@@ -62,7 +62,9 @@ struct SPlanes {
         return lo | (read64(k, 0) << avail);
     }
 };
-enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5 };
+// PL_BLK: scratch plane of the backward list's batch collection ("one sample below a pending member"), kept in what was
+// the list prefetch ring of sto_qss_memo.cuh's kernels (2 KB per warp >= 8 NW cpw bytes for NW <= 64, cpw <= 4).
+enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5, PL_BLK = 6 };
 
 // The front step with its independent sub-chains free to overlap.  eval_core (sto_qss_memo.cuh) is three divisions and
 // five square roots that nvcc expands into fast path + guarded call to a slow path each: no two of them overlap in one
@@ -247,6 +249,9 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
     // profiling build (tools/phase_profile.py): [4 * k + phase], k = 0 search clocks, 1 evaluate clocks, 2 commit + post
     // clocks, 3 evaluation rounds of the warp
     long long clk2[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long clk3[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 set-up, 1 phase entry (word scans, sweep0), 2 fold, 3 finish, 4 whole kernel
+    const long long t_begin = clock64();
+    long long t3 = t_begin;
     long long t2 = clock64();
 #endif
     if (active) {
@@ -263,9 +268,13 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             P.set_word(PL_LIVE0, w, ones); P.set_word(PL_LIVE1, w, ones);
             P.set_word(PL_CONT0, w, 0); P.set_word(PL_CONT1, w, 0);
             P.set_word(PL_STOP0, w, 0); P.set_word(PL_STOP1, w, 0);
+            P.set_word(PL_BLK, w, 0);
         }
     }
     __syncwarp();
+#if defined(STO_PHASE_CLOCKS)
+    { const long long c_ = clock64(); clk3[0] += c_ - t3; t3 = c_; }
+#endif
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
     u64 wordsB = (NW >= 64) ? ~0ull : ((1ull << NW) - 1ull), wordsF = wordsB;   // words with running fronts (NW <= 64)
     int nB = 0, nF = 0;    // live re-spawned fronts per direction
@@ -280,23 +289,26 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
         int w = 0;
         bool open = false, skip = false;
         int32_t* list = LB;                      // re-spawned lists: cursor r, write position wr
-        int nlist = 0, r = 0, wr = 0, held = -2;
-        int mine = 0, cur = 0, nxt = 0;          // phase 3: the entry this lane holds (index, value), the one after it
-        int chunk = 0, nchunk = 0;               // phase 1: entries (r & ~(G-1)) + g and the same of the next chunk
+        int nlist = 0, r = 0, wr = 0;
+        int mine = 0, cur = 0, nxt = 0;          // phases 1, 3: the entry this lane holds (index, value), the one after it
         int phase = 0;
         bool entering = true;
         for (;;) {
             if (entering) {
                 entering = false;
+#if defined(STO_PHASE_CLOCKS)
+                t3 = clock64();
+#endif
                 if (phase == 0) {
                     skip = done || nliveB == 0;
                     todo = memo2_scan_words<G>(P, false, skip, s, g, wordsB, steps);
                     open = false;
                 } else if (phase == 1) {
                     if (!warp_any(!done && nB > 0)) { phase = 2; entering = true; continue; }
-                    list = LB; nlist = done ? 0 : nB; r = 0; wr = 0; held = -2;
-                    chunk = (g < nlist) ? list[g] : -1;
-                    nchunk = (G + g < nlist) ? list[G + g] : -1;
+                    list = LB; nlist = done ? 0 : nB; r = 0; wr = 0;
+                    mine = g;
+                    cur = (mine < nlist) ? list[mine] : 0;
+                    nxt = (mine + G < nlist) ? list[mine + G] : 0;
                 } else if (phase == 2) {
                     if (iters == 0 && !done && nliveF == N) {
                         const Sweep0Out o = memo2_sweep0(A, V, rec, P, lat0, nliveF, steps, status);
@@ -316,6 +328,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             const bool fwd = phase >= 2;
 #if defined(STO_PHASE_CLOCKS)
             t2 = clock64();
+            if (t3) { clk3[1] += t2 - t3; t3 = 0; }
 #endif
             // ---- search: the front(s) of this candidate that need an evaluation now
             bool has = false, kill = false, committer = false;
@@ -356,46 +369,88 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 }
                 committer = has;
             } else if (phase == 1) {
-                // backward re-spawned list: a batch ends before a front one sample below a pending member (its source
-                // sample would be written); lane k keeps member k, one vote per entry
+                // Backward re-spawned list, collected G entries per step (lane (r + k) mod G holds entry r + k, as in phase 3).
+                // A batch takes fronts that need an evaluation until it has G of them or meets a front one sample below a
+                // pending member (that member will write the front's source sample): members of earlier steps are remembered
+                // in the BLOCKED plane (bit p_member - 1), members of the same step are compared by shuffles.
                 int cnt = 0, my_p = -1, my_slot = -1;
                 bool closed = false;
                 for (;;) {
-                    const bool act = !closed && cnt < G && (held != -2 || r < nlist);
+                    const bool act = !closed && cnt < G && r < nlist;
                     if (!warp_any(act)) break;
-                    const int e = __shfl_sync(full, chunk, lane0 + (r & (G - 1)));
-                    int iv = -1;
-                    if (act) {
-                        if (held != -2) { iv = held; held = -2; }
-                        else {
-                            iv = e;
-                            ++r;
-                            if ((r & (G - 1)) == 0) {            // crossed into the next chunk
-                                chunk = nchunk;
-                                nchunk = (r + G + g < nlist) ? list[r + G + g] : -1;
-                            }
-                        }
-                    }
-                    const bool have = act && iv >= 0;            // (iv < 0: tombstone of an earlier walk)
-                    int pp = have ? iv - s : 0;
+                    const int rot = r & (G - 1);
+                    const int k = (mine - r) & (G - 1);          // window position of this lane's entry
+                    const int left = nlist - r, nv = (left < G) ? ((left > 0) ? left : 0) : G;
+                    const bool live_e = act && k < nv && cur >= 0;   // (cur < 0: tombstone of an earlier walk, dropped silently)
+                    int pp = live_e ? cur - s : 0;
                     if (pp < 0) pp += N;
-                    bool hit = false;
-                    if (have && g < cnt) { const int pam = (my_p == 0) ? N - 1 : my_p - 1; hit = pp == pam; }
-                    const bool conflict = ((__ballot_sync(full, hit) >> lane0) & gbits) != 0u;
-                    if (have) {
-                        if (conflict) { held = iv; closed = true; }
-                        else {
-                            ++steps;
-                            const bool c0 = P.test(PL_CONT0, pp), s0 = P.test(PL_STOP0, pp);
-                            if (c0) { if (wr != r - 1 && g == 0) list[wr] = iv; ++wr; }
-                            else if (!s0) {
-                                if (g == cnt) { my_p = pp; my_slot = wr; }
-                                if (wr != r - 1 && g == 0) list[wr] = iv;   // slot reserved; a tombstone replaces it if the front stops
-                                ++wr;
-                                ++cnt;
-                            }
+                    const bool c0 = P.test(PL_CONT0, pp), s0 = P.test(PL_STOP0, pp), bl = P.test(PL_BLK, pp);
+                    const bool pend = live_e && !c0 && !s0;
+                    unsigned m_pend = (__ballot_sync(full, pend) >> lane0) & gbits;
+                    unsigned m_keep = (__ballot_sync(full, live_e && c0) >> lane0) & gbits;
+                    unsigned m_live = (__ballot_sync(full, live_e) >> lane0) & gbits;
+                    if (rot) {                                   // bit j = entry r + j
+                        m_pend = ((m_pend >> rot) | (m_pend << (G - rot))) & gbits;
+                        m_keep = ((m_keep >> rot) | (m_keep << (G - rot))) & gbits;
+                        m_live = ((m_live >> rot) | (m_live << (G - rot))) & gbits;
+                    }
+                    // an EARLIER pending entry of this window one sample above this one?  (p_j - 1 == p_i)
+                    bool conf = live_e && bl;
+                    int ppn = pp + 1;
+                    if (ppn == N) ppn = 0;
+#pragma unroll
+                    for (int dlt = 1; dlt < G; ++dlt) {
+                        const int pj = __shfl_sync(full, pp, lane0 + ((g - dlt) & (G - 1)));   // entry k - dlt sits dlt lanes below
+                        if (dlt <= k && ((m_pend >> (k - dlt)) & 1u) && pj == ppn) conf = conf || live_e;
+                    }
+                    unsigned m_conf = (__ballot_sync(full, conf) >> lane0) & gbits;
+                    if (rot) m_conf = ((m_conf >> rot) | (m_conf << (G - rot))) & gbits;
+                    const int fc = m_conf ? (__ffs(m_conf) - 1) : nv;           // the batch must end before entry r + fc
+                    const unsigned below_fc = (fc >= 32) ? full : ((1u << fc) - 1u);
+                    const int room = G - cnt;
+                    int end = fc;
+                    {
+                        unsigned x = m_pend & below_fc;
+                        if (__popc(x) > room) {                  // more fronts to evaluate than lanes left: stop after the room-th
+                            for (int i2 = 1; i2 < room; ++i2) x &= x - 1u;
+                            end = __ffs(x);
                         }
                     }
+                    const unsigned cons = (end >= 32) ? full : ((1u << end) - 1u);
+                    const unsigned m_kept = (m_keep | m_pend) & cons;
+                    if (live_e && k < end && (c0 || pend)) {
+                        const int dst = wr + __popc(m_kept & ((1u << k) - 1u));
+                        if (dst != mine) list[dst] = cur;        // a member's slot is reserved; a tombstone replaces it if it stops
+                    }
+                    // the j-th new member becomes member cnt + j: lane cnt + j of the group learns its sample and slot
+                    const unsigned m_new = m_pend & cons;
+                    const int nnewm = __popc(m_new);
+                    const bool newm = act && g >= cnt && g < cnt + nnewm;
+                    int jpos = 0;
+                    if (newm) {
+                        unsigned x = m_new;
+                        for (int i2 = 0; i2 < g - cnt; ++i2) x &= x - 1u;
+                        jpos = __ffs(x) - 1;
+                    }
+                    const int p_m = __shfl_sync(full, pp, lane0 + ((rot + jpos) & (G - 1)));
+                    if (newm) {
+                        my_p = p_m;
+                        my_slot = wr + __popc(m_kept & ((1u << jpos) - 1u));
+                        P.atom_set(PL_BLK, (p_m == 0) ? N - 1 : p_m - 1);
+                    }
+                    if (act) {
+                        steps += __popc(m_live & cons);
+                        wr += __popc(m_kept);
+                        cnt += nnewm;
+                        r += end;
+                        closed = end < nv && end == fc;          // stopped at a conflicting entry (it opens the next batch)
+                        if (k < end) {
+                            mine += G;
+                            cur = nxt;
+                            nxt = (mine + G < nlist) ? list[mine + G] : 0;
+                        }
+                    }
+                    __syncwarp();                                // the BLOCKED bits of the new members, before the next step tests them
                 }
                 has = g < cnt;
                 p = has ? my_p : 0;
@@ -564,7 +619,8 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     if (w == 0 && (chg_b & 1u) && row0) todo |= 1ull << (NW - 1);
                 }
             } else if (phase == 1) {
-                if (status != 0) { nlist = r; held = -2; }   // abandon the walk of a failed candidate
+                if (has) P.atom_clear(PL_BLK, (p == 0) ? N - 1 : p - 1);   // the batch is committed: nothing is blocked any more
+                if (status != 0) nlist = r;                  // abandon the walk of a failed candidate
             } else if (phase == 2) {
                 if (has) {
                     att &= ~bit;
@@ -585,6 +641,9 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             STO2_CLK(8 + phase)
         }
         __syncwarp();   // list entries stored by one lane are read by another in the fold / the next walk
+#if defined(STO_PHASE_CLOCKS)
+        t3 = clock64();
+#endif
         if (!done && wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
         {
             // fold the rows spawned in this iteration behind both lists (simulator.py:351-356), G rows at a time.  The move is
@@ -612,11 +671,23 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             ++iters;
             if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
         }
+#if defined(STO_PHASE_CLOCKS)
+        { const long long c_ = clock64(); clk3[2] += c_ - t3; t3 = 0; }
+#endif
     }
+#if defined(STO_PHASE_CLOCKS)
+    t3 = clock64();
+#endif
     qss_finish_group<G>(A, rec, b, active, status, steps, iters, g, lane0);
 #if defined(STO_PHASE_CLOCKS)
     if (active && g == 0 && A.summary) for (int k = 0; k < 8; ++k) A.summary[at(k, ld, b)] = (double)clk2[k];
     if (active && g == 0 && A.lat) for (int k = 0; k < 8; ++k) A.lat[at(k, ld, b)] = (double)clk2[8 + k];
+    {
+        const long long c_ = clock64();
+        clk3[3] = c_ - t3;
+        clk3[4] = c_ - t_begin;
+    }
+    if (active && g == 0 && A.tseg) for (int k = 0; k < 8; ++k) A.tseg[at(k, ld, b)] = (double)clk3[k];
 #endif
 }
 
