@@ -396,52 +396,84 @@ def run_gpu_arm(args):
         else:
             d_off.append([candidates.smooth_offsets_device(M, lo + a, lo + b, rt.dist_to_left, rt.dist_to_right, dev,
                                                            seed=1234 + 104729 * j) for a, b in cuts])
-    lap = torch.empty(B, dtype=torch.float64, device=dev)
-    st = torch.empty(B, dtype=torch.int32, device=dev)
-    lap_ld = [torch.empty(((b - a + 31) & ~31), dtype=torch.float64, device=dev) for a, b in cuts]
-    st_ld = [torch.empty(((b - a + 31) & ~31), dtype=torch.int32, device=dev) for a, b in cuts]
-    pair_argmin = sharding.DeviceArgmin(dev)
-    best = torch.empty(1, dtype=torch.float64, device=dev)
-    best_idx = torch.empty(1, dtype=torch.int64, device=dev)
+    # Steps are software-pipelined over two CUDA streams: step k+1's fit / sampler / QSS start while the slowest warps of
+    # step k's QSS are still running (a QSS launch ends with its hardest candidates; the SMs the others leave are idle
+    # otherwise).  Each stream has its own workspace, outputs and reduction buffers; every step is a complete pass.  The
+    # strictly serial figure (one step at a time on one stream) is reported next to it (`serial`).
+    n_slots = 2 if (args.pipeline and 2.0 * per_cand * chunk <= 40e9) else 1
 
-    def evaluate(j):
+    class Slot:
+        def __init__(self, k):
+            self.ev = ev if k == 0 else BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), veh,
+                                                             bank=bank, device=dev, impl=args.qss)
+            self.stream = torch.cuda.Stream(device=dev) if n_slots > 1 else torch.cuda.current_stream(dev)
+            self.lap = torch.empty(B, dtype=torch.float64, device=dev)
+            self.st = torch.empty(B, dtype=torch.int32, device=dev)
+            self.lap_ld = [torch.empty(((b - a + 31) & ~31), dtype=torch.float64, device=dev) for a, b in cuts]
+            self.st_ld = [torch.empty(((b - a + 31) & ~31), dtype=torch.int32, device=dev) for a, b in cuts]
+            self.pair_argmin = sharding.DeviceArgmin(dev)
+            self.best = torch.empty(1, dtype=torch.float64, device=dev)
+            self.best_idx = torch.empty(1, dtype=torch.int64, device=dev)
+
+    slots = [Slot(k) for k in range(n_slots)]
+    lap_ld, st_ld = slots[0].lap_ld, slots[0].st_ld
+
+    def evaluate(j, S=None):
+        S = S or slots[0]
         for k, (a, b) in enumerate(cuts):
-            l, s = ev.lap_times(d_off[j % n_sets][k], B=b - a, out=lap_ld[k], status=st_ld[k])
+            l, s = S.ev.lap_times(d_off[j % n_sets][k], B=b - a, out=S.lap_ld[k], status=S.st_ld[k])
             if len(cuts) > 1:
-                lap[a:b].copy_(l)
-                st[a:b].copy_(s)
-        return (lap, st) if len(cuts) > 1 else (lap_ld[0][:B], st_ld[0][:B])
+                S.lap[a:b].copy_(l)
+                S.st[a:b].copy_(s)
+        return (S.lap, S.st) if len(cuts) > 1 else (S.lap_ld[0][:B], S.st_ld[0][:B])
 
-    def reduce(l, s):
+    def reduce(l, s, S=None):
+        S = S or slots[0]
         if W["reduce"] == "pair":      # one (best lap, global index) pair per rank: 16-byte all-gather, argmin
-            return pair_argmin(l, s, lo)
+            return S.pair_argmin(l, s, lo)
         # the lap vector of the whole job on every rank (8 B per candidate over NVLink), argmin there; failed candidates
         # travel as NaN, which the argmin ignores
         full = sharding.all_gather_laps(torch.where(s == 0, l, torch.full_like(l, float("nan"))), total)
-        _lib.check(lib.sto_argmin_f64(ctypes.c_void_p(full.data_ptr()), None, total, ctypes.c_void_p(best.data_ptr()),
-                                      ctypes.c_void_p(best_idx.data_ptr()),
+        _lib.check(lib.sto_argmin_f64(ctypes.c_void_p(full.data_ptr()), None, total, ctypes.c_void_p(S.best.data_ptr()),
+                                      ctypes.c_void_p(S.best_idx.data_ptr()),
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return best, best_idx
+        return S.best, S.best_idx
 
-    def step(j):
-        return reduce(*evaluate(j))
+    def step(j, S=None):
+        return reduce(*evaluate(j, S), S)
+
+    def run_steps(n, pipelined):
+        """n complete steps; returns (elapsed ms on the device, the last step's winner)."""
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(dev)
+        t0e.record(cur)
+        win = None
+        if pipelined and n_slots > 1:
+            for S in slots:
+                S.stream.wait_event(t0e)
+            for j in range(n):
+                S = slots[j % n_slots]
+                with torch.cuda.stream(S.stream):
+                    win = step(j, S)
+            for S in slots:
+                cur.wait_stream(S.stream)
+        else:
+            for j in range(n):
+                win = step(j)
+        t1e.record(cur)
+        return t0e, t1e, win
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for j in range(args.warmup):
-        step(j)
+    run_steps(args.warmup, True)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for j in range(args.steps):
-        winner = step(j)
-    e1.record()
+    e0, e1, winner = run_steps(args.steps, True)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -452,6 +484,19 @@ def run_gpu_arm(args):
     # otherwise stretch every synchronous host call of the e2e leg below
     clocks = sampler.stop() if rank == 0 else None
     win_lap, win_idx = float(winner[0].item()), int(winner[1].item())
+    serial = None
+    if n_slots > 1:   # the same steps strictly one at a time
+        n_ser = min(args.steps, 6)
+        run_steps(2, False)
+        barrier()
+        s0, s1, _w = run_steps(n_ser, False)
+        barrier()
+        ms_s = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+        serial = {"steps": n_ser, "ms_per_step": float(ms_s.item()) / n_ser,
+                  "value": total * n_ser / (float(ms_s.item()) * 1e-3), "unit": UNIT,
+                  "note": "one step at a time on one stream (no overlap between consecutive steps)"}
 
     # ---- e2e: host buffers through the C ABI (H2D of the offsets + transpose + D2H of laps inside the call), then the
     # same exchange as above starting from the host laps
@@ -578,6 +623,9 @@ def run_gpu_arm(args):
         "config": {"workload": W["text"], "config_id": cfg, "candidates_total": total, "candidates_per_gpu": B,
                    "candidates_per_launch": chunk, "launches_per_step": len(cuts), "M": M, "N": N,
                    "qss_impl": args.qss, "bank": bank is not None,
+                   "pipelining": ("consecutive steps alternate between two CUDA streams (own workspace each): step k+1 starts "
+                                  "under the tail of step k's QSS; every step is a complete pass; serial figure in `serial`"
+                                  if n_slots > 1 else "none (one stream)"),
                    "fit_solver": "fitpack: FITPACK's fpclos Givens sweep restated bit for bit (coefficients identical "
                                  "to the reference's scipy splprep)",
                    "l2": ("two alternating candidate sets" if n_sets == 2 else "one candidate set of %.1f GB (>> 126 MB L2)"
@@ -612,6 +660,7 @@ def run_gpu_arm(args):
                  "note": "70 flop per front step of the reference's schedule; the memoised kernel evaluates ~6 % of them "
                          "(bit-identical result), so its executed FP64 work is ~17x lower: the path is bound by per-line "
                          "dependent chains of divisions / square roots, neither roof"},
+        "serial": serial,
         "parity": parity,
         "winner": {"lap_s": win_lap, "candidate": win_idx},
         "clocks": clocks,
@@ -665,6 +714,8 @@ def main():
                     help="candidates per GPU (config 1) / in total (configs 2-4); 0 = the configuration's own size")
     ap.add_argument("--launch-gb", type=float, default=56.0, help="device workspace budget of one launch")
     ap.add_argument("--parity", type=int, default=0, help="candidates checked against the oracle (0 = choose)")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="run the timed steps strictly one at a time (default: two-stream software pipelining)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the separately-reported fast-mode block")
     ap.add_argument("--large-batch", type=int, default=32768,
