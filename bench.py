@@ -400,7 +400,7 @@ def run_gpu_arm(args):
     # step k's QSS are still running (a QSS launch ends with its hardest candidates; the SMs the others leave are idle
     # otherwise).  Each stream has its own workspace, outputs and reduction buffers; every step is a complete pass.  The
     # strictly serial figure (one step at a time on one stream) is reported next to it (`serial`).
-    n_slots = 2 if (args.pipeline and 2.0 * per_cand * chunk <= 40e9) else 1
+    n_slots = args.slots if (args.pipeline and args.slots * per_cand * chunk <= 40e9) else 1
 
     class Slot:
         def __init__(self, k):
@@ -511,30 +511,57 @@ def run_gpu_arm(args):
     lap_dev = torch.empty(B, dtype=torch.float64, device=dev)
     st_dev = torch.empty(B, dtype=torch.int32, device=dev)
 
-    def e2e_step(j):
-        ev.lap_times_host_into(pinned[j % n_sets].data_ptr(), B, lap_pin.data_ptr(), st_pin.data_ptr(),
+    def e2e_step(j, bufs):
+        lp, sp = bufs
+        ev.lap_times_host_into(pinned[j % n_sets].data_ptr(), B, lp.data_ptr(), sp.data_ptr(),
                                int(args.launch_gb * 2 ** 30))
         if world > 1:
-            lap_dev.copy_(lap_pin, non_blocking=True)
-            st_dev.copy_(st_pin, non_blocking=True)
+            lap_dev.copy_(lp, non_blocking=True)
+            st_dev.copy_(sp, non_blocking=True)
             b_, i_ = reduce(lap_dev, st_dev)
             return float(b_.item())                           # the step's result is consumed on the host
-        return float(np.nanmin(lap_pin.numpy()))
+        return float(np.nanmin(lp.numpy()))
 
-    for j in range(min(args.warmup, 2)):
-        e2e_step(j)
+    # Two host threads drive the GPU when the steps are pipelined (the library keeps two contexts per device: the calls
+    # overlap on two streams); every call is the plain synchronous sto_lap_time_host_f64 on its own pinned buffers.
+    n_thr = 2 if (n_slots > 1 and world == 1) else 1
+    bufs = [(lap_pin, st_pin)] + [(torch.empty(B, dtype=torch.float64).pin_memory(),
+                                   torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(n_thr - 1)]
+    e2e_calls = []
+
+    def e2e_run(n, record):
+        def worker(t):
+            for j in range(t, n, n_thr):
+                tc = time.perf_counter()
+                e2e_step(j, bufs[t])
+                if record:
+                    e2e_calls.append(1e3 * (time.perf_counter() - tc))
+        if n_thr == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(t,)) for t in range(n_thr)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
+    e2e_run(max(min(args.warmup, 2), n_thr), False)
     barrier()
     t0 = time.perf_counter()
-    e2e_calls = []
-    for j in range(args.steps):
-        tc = time.perf_counter()
-        e2e_step(j)
-        e2e_calls.append(1e3 * (time.perf_counter() - tc))
+    e2e_run(args.steps, True)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = total * args.steps / float(e2e_s.item())
+    e2e_one = None
+    if n_thr > 1:   # the same calls from one thread, back to back
+        n1 = min(args.steps, 6)
+        t1 = time.perf_counter()
+        for j in range(n1):
+            e2e_step(j, bufs[0])
+        e2e_one = {"value": total * n1 / (time.perf_counter() - t1), "unit": UNIT, "calls": n1,
+                   "note": "one host thread, one call at a time"}
     del pinned
 
     # ---- roofline leg: per-kernel durations from CUDA events recorded on the launching stream inside the library
@@ -623,7 +650,7 @@ def run_gpu_arm(args):
         "config": {"workload": W["text"], "config_id": cfg, "candidates_total": total, "candidates_per_gpu": B,
                    "candidates_per_launch": chunk, "launches_per_step": len(cuts), "M": M, "N": N,
                    "qss_impl": args.qss, "bank": bank is not None,
-                   "pipelining": ("consecutive steps alternate between two CUDA streams (own workspace each): step k+1 starts "
+                   "pipelining": ("consecutive steps rotate over %d CUDA streams (own workspace each): step k+1 starts " % n_slots +
                                   "under the tail of step k's QSS; every step is a complete pass; serial figure in `serial`"
                                   if n_slots > 1 else "none (one stream)"),
                    "fit_solver": "fitpack: FITPACK's fpclos Givens sweep restated bit for bit (coefficients identical "
@@ -636,7 +663,10 @@ def run_gpu_arm(args):
                                    "on every rank")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * M * B + (12 * B if world > 1 else 0)),
                 "d2h_bytes_per_step": int(12 * B + (16 if world > 1 else 0)),
+                "host_threads": n_thr, "one_thread": e2e_one,
                 "api": "sto_lap_time_host_f64 (pinned host offsets [B][M] in, lap/status out)"
+                       + (", called from %d host threads (two contexts per device in the library: the calls overlap)" % n_thr
+                          if n_thr > 1 else "")
                        + ("; then H2D of the laps, the same NCCL exchange, D2H of the winner" if world > 1 else ""),
                 "ms_per_call": [round(x, 2) for x in e2e_calls]},
         "gpu_launches": int((4 * len(cuts) + (3 if W["reduce"] == "pair" else 1)) * args.steps),
@@ -714,6 +744,7 @@ def main():
                     help="candidates per GPU (config 1) / in total (configs 2-4); 0 = the configuration's own size")
     ap.add_argument("--launch-gb", type=float, default=56.0, help="device workspace budget of one launch")
     ap.add_argument("--parity", type=int, default=0, help="candidates checked against the oracle (0 = choose)")
+    ap.add_argument("--slots", type=int, default=2, help="streams the steps are pipelined over")
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="run the timed steps strictly one at a time (default: two-stream software pipelining)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

