@@ -79,7 +79,11 @@ __device__ __noinline__ EvalRes eval_core_plain(const sto_vehicle_f64& V, bool f
     return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
 }
 __device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
-                                                 double aq_old, double dd, double Rq, double gq, double lat0) {
+                                                 double aq_old, double dd, double Rq, double gq, double lat0,
+                                                 long long* slow_cnt = nullptr) {
+    // general speed tables (more than three rows: a data-dependent interval search) take the plain path; the reference's
+    // own 3-row tables - everywhere in its tests and examples - are one compare (ppoly4's n == 2 case)
+    if ((V.n_acc != 3) | (V.n_dcc != 3)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
     bool slow = false;
     const double dt = div_fast(dd, vp, slow);                                     // front_step_rt: dt = dd / vp
     const double l = np_clip(ap, V.max_lon_dcc, V.max_lon_acc);                   // max_lat_acc(V, ap)
@@ -87,8 +91,21 @@ __device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool 
     const double ell = V.max_left_acc * sqrt_fast(1.0 - div_fast(l * l, Lx * Lx, slow), slow);
     const double mc = sqrt_fast(fabs(fabs(ell) - gq) * Rq, slow);                 // calc_v(max_lat_acc, Rq, gq)
     const double vinit = sqrt_fast(fabs(fabs(lat0) - gq) * Rq, slow);             // init_speed's calc_v (used on a re-spawn)
-    const double vacc = ppoly4(V.acc_x, V.acc_c, V.n_acc, vp);
-    const double vdcc = ppoly4(V.dcc_x, V.dcc_c, V.n_dcc, vp);
+    double vacc, vdcc;
+    {   // ppoly4 for a 3-row table, straight line (a NaN speed raises `slow` in the division above and is redone)
+        const int ia = (vp >= V.acc_x[1]) ? 1 : 0, id = (vp >= V.dcc_x[1]) ? 1 : 0;
+        const double sa = vp - V.acc_x[ia], sd = vp - V.dcc_x[id];
+        double ra = 0.0, za = 1.0, rd = 0.0, zd = 1.0;
+        ra = ra + V.acc_c[3][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[3][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[2][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[2][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[1][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[1][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[0][ia] * za;
+        rd = rd + V.dcc_c[0][id] * zd;
+        vacc = ra; vdcc = rd;
+    }
     const double md = dt * V.max_jerk;
     double hi = ap + md, lo = ap - md;
     hi = np_clip(hi, vdcc, vacc);
@@ -103,7 +120,10 @@ __device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool 
     const bool valid = smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
     const double gg = g * g;
     const double aq = div_fast(fwd ? gg - vp2 : vp2 - gg, 2 * dd, slow);
-    if (slow || vp == 0.0) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+#if defined(STO_PHASE_CLOCKS)
+    if (slow_cnt && (slow | (vp == 0.0))) *slow_cnt += 1;
+#endif
+    if (slow | (vp == 0.0)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
     EvalRes r;
     r.v_new = 0.0; r.a_new = 0.0;
     if (valid) {
@@ -119,12 +139,27 @@ __device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool 
     return r;
 }
 __device__ __forceinline__ EvalRes eval_pure_ilp(const QssArgs& A, const sto_vehicle_f64& V, const double* rec, bool fwd,
-                                                 int p, int q, double lat0) {
+                                                 int p, int q, double lat0, long long* load_clk = nullptr) {
     const double* rp = rec + 4 * (size_t)p;     // both 32-byte records are fetched up front: one overlapped round trip
     const double* rq = rec + 4 * (size_t)q;
     const double vp = rp[0], ap = rp[1], ddp = rp[2];
     const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
     const double dd = fwd ? ddp : ddq;          // the chord between p and q is stored at the lower sample
+#if defined(STO_PHASE_CLOCKS)
+    if (load_clk) {   // profiling build: when have the seven loads arrived?  (a compare that needs them, then the clock)
+        const long long c0_ = clock64();
+        bool odd = (__double_as_longlong(vp) ^ __double_as_longlong(vq) ^ __double_as_longlong(Rq) ^
+                    __double_as_longlong(ddp) ^ __double_as_longlong(ddq) ^ __double_as_longlong(ap) ^
+                    __double_as_longlong(aq_old)) == 0x7ff8dead12345678ll;
+        if (odd) *load_clk += 1;
+        *load_clk += clock64() - c0_;
+        const long long c1_ = clock64();
+        const EvalRes r_ = eval_core_ilp(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0, load_clk + 1);
+        if (r_.kind == 99) load_clk[2] += 1;      // (never true: the result is needed before the clock below is read)
+        load_clk[2] += clock64() - c1_;
+        return r_;
+    }
+#endif
     return eval_core_ilp(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);
 }
 
@@ -552,7 +587,11 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             res.kind = EV_NONE; res.v_new = 0.0; res.a_new = 0.0;
             if (has) {
                 if (kill) res.kind = EV_KILL;
+#if defined(STO_PHASE_CLOCKS)
+                else res = eval_pure_ilp(A, V, rec, fwd, p, q, lat0, &clk3[5]);
+#else
                 else res = eval_pure_ilp(A, V, rec, fwd, p, q, lat0);
+#endif
             }
             __syncwarp();
             STO2_CLK(4 + phase)

@@ -61,7 +61,8 @@ else:
               % (ph[p_], 100 * se / tot, 100 * ev / tot, 100 * co / tot, rd, se / max(rd, 1), ev / max(rd, 1), co / max(rd, 1)))
     oth = res["time"][:8, :B].cpu().numpy()
     names3 = ["set-up (records, planes)", "phase entry (word scans, sweep0, list heads)", "fold + iteration tail", "finish (fill_time, lap)",
-              "whole kernel"]
+              "whole kernel", "record loads in flight (all evaluations of this lane)", "evaluations redone with the plain operators (count)",
+              "arithmetic of the evaluations (clocks, this lane)"]
     for k, n in enumerate(names3):
         print("%-46s mean %.3g  max %.3g clocks  (%.2f / %.2f ms)" % (n, oth[k].mean(), oth[k].max(), oth[k].mean() / 1.965e6, oth[k].max() / 1.965e6))
     print("round loop, max over candidates: %.2f ms" % (allv[:12].sum(axis=0).max() / 1.965e6))
