@@ -22,6 +22,7 @@
 #include "sto_eval.cuh"
 #include "sto_fit.cuh"
 #include "sto_qss.cuh"
+#include "sto_qss_memo.cuh"
 
 namespace sto {
 
@@ -44,6 +45,12 @@ STO_HD bool fast_same_bits(double a, double b) {
 template <bool FWD>
 STO_HD void sweep_step(const sto_vehicle_f64& V, double lat0, double vp, double ap, double dd, double Rq, double gq,
                        double& vq, double& aq, int& status) {
+#if defined(__CUDA_ARCH__)
+    // the same step with its independent chains overlapped (eval_core_ilp, sto_qss_memo.cuh: identical bits)
+    const EvalRes r = eval_core_ilp(V, FWD, vp, ap, vq, aq, dd, Rq, gq, lat0);
+    if (r.kind == EV_ZERO) status |= STO_CAND_ZERO_SPEED;
+    else if (r.kind != EV_STOP) { vq = r.v_new; aq = r.a_new; }   // WRITE / KEEP: (g, a); SPAWN / RESPAWN: fresh turn, a = 0
+#else
     if (vp == 0.0) { status |= STO_CAND_ZERO_SPEED; return; }   // the reference raises here (simulator.py:164-165)
     double g, vp2;
     bool respawn;
@@ -57,6 +64,7 @@ STO_HD void sweep_step(const sto_vehicle_f64& V, double lat0, double vp, double 
         vq = init_speed(lat0, Rq, gq, V.max_speed);
         aq = 0.0;
     }
+#endif
 }
 
 #ifndef STO_FAST_CHUNK

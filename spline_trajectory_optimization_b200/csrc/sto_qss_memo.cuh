@@ -281,6 +281,81 @@ STO_HD EvalRes eval_core(const sto_vehicle_f64& V, bool fwd, double vp, double a
     return r;
 }
 
+#if defined(__CUDACC__)
+// The front step with its independent sub-chains free to overlap.  eval_core (sto_qss_memo.cuh) is three divisions and
+// five square roots that nvcc expands into fast path + guarded call to a slow path each: no two of them overlap in one
+// warp, ~1,500 cycles of dependent latency per evaluation on the critical path of every round.  Here the SAME operations
+// in the SAME order per value (every result is bit-identical) are written with the flagged branch-free division / square
+// root of sto_common.cuh (identical bits while the operand-range flag is down; sto_selftest_fp64), so the compiler sees one
+// basic block in which  dd / v -> jerk window -> state speeds,  friction ellipse -> curve speed,  the two table look-ups
+// and the re-initialisation speed  run side by side (~500 cycles of dependent latency).  Anything unusual - a raised flag
+// (zero / infinite / denormal / NaN operand), v_p == 0 - is redone out of line with the plain operators.
+__device__ __noinline__ EvalRes eval_core_plain(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
+                                                double aq_old, double dd, double Rq, double gq, double lat0) {
+    return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+}
+__device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
+                                                 double aq_old, double dd, double Rq, double gq, double lat0,
+                                                 long long* slow_cnt = nullptr) {
+    // general speed tables (more than three rows: a data-dependent interval search) take the plain path; the reference's
+    // own 3-row tables - everywhere in its tests and examples - are one compare (ppoly4's n == 2 case)
+    if ((V.n_acc != 3) | (V.n_dcc != 3)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+    bool slow = false;
+    const double dt = div_fast(dd, vp, slow);                                     // front_step_rt: dt = dd / vp
+    const double l = np_clip(ap, V.max_lon_dcc, V.max_lon_acc);                   // max_lat_acc(V, ap)
+    const double Lx = (l > 0.0) ? V.max_lon_acc : V.max_lon_dcc;
+    const double ell = V.max_left_acc * sqrt_fast(1.0 - div_fast(l * l, Lx * Lx, slow), slow);
+    const double mc = sqrt_fast(fabs(fabs(ell) - gq) * Rq, slow);                 // calc_v(max_lat_acc, Rq, gq)
+    const double vinit = sqrt_fast(fabs(fabs(lat0) - gq) * Rq, slow);             // init_speed's calc_v (used on a re-spawn)
+    double vacc, vdcc;
+    {   // ppoly4 for a 3-row table, straight line (a NaN speed raises `slow` in the division above and is redone)
+        const int ia = (vp >= V.acc_x[1]) ? 1 : 0, id = (vp >= V.dcc_x[1]) ? 1 : 0;
+        const double sa = vp - V.acc_x[ia], sd = vp - V.dcc_x[id];
+        double ra = 0.0, za = 1.0, rd = 0.0, zd = 1.0;
+        ra = ra + V.acc_c[3][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[3][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[2][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[2][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[1][ia] * za;  za *= sa;
+        rd = rd + V.dcc_c[1][id] * zd;  zd *= sd;
+        ra = ra + V.acc_c[0][ia] * za;
+        rd = rd + V.dcc_c[0][id] * zd;
+        vacc = ra; vdcc = rd;
+    }
+    const double md = dt * V.max_jerk;
+    double hi = ap + md, lo = ap - md;
+    hi = np_clip(hi, vdcc, vacc);
+    lo = np_clip(lo, vdcc, vacc);
+    const double vp2 = vp * vp;
+    const double th = 2 * hi * dd, tl = 2 * lo * dd;
+    const double s_hi = sqrt_fast(py_max(fwd ? th + vp2 : vp2 - th, 0.0), slow);
+    const double s_lo = sqrt_fast(py_max(fwd ? tl + vp2 : vp2 - tl, 0.0), slow);
+    const double smax = fwd ? s_hi : s_lo, smin = fwd ? s_lo : s_hi;
+    const double g = py_min3(smax, mc, V.max_speed);
+    const bool respawn = (g > mc) || (g < smin);
+    const bool valid = smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
+    const double gg = g * g;
+    const double aq = div_fast(fwd ? gg - vp2 : vp2 - gg, 2 * dd, slow);
+#if defined(STO_PHASE_CLOCKS)
+    if (slow_cnt && (slow | (vp == 0.0))) *slow_cnt += 1;
+#endif
+    if (slow | (vp == 0.0)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
+    EvalRes r;
+    r.v_new = 0.0; r.a_new = 0.0;
+    if (valid) {
+        if (vq < g) { r.kind = EV_STOP; return r; }
+        r.v_new = g; r.a_new = aq;
+        r.kind = (!same_bits(vq, g) || !same_bits(aq_old, aq)) ? EV_WRITE : EV_KEEP;
+        return r;
+    }
+    if (fwd || !respawn) { r.kind = EV_STOP; return r; }
+    const double vi = (V.max_speed < vinit) ? V.max_speed : vinit;
+    r.v_new = vi;
+    r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;
+    return r;
+}
+#endif
+
 STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool fwd, int p, int q, double lat0) {
     const int N = A.N;
     // both 32-byte records are fetched up front (adjacent in memory): one overlapped round trip per evaluation
@@ -290,7 +365,11 @@ STO_HD EvalRes eval_pure(const QssArgs& A, const sto_vehicle_f64& V, int b, bool
     const double vp = rp[0], ap = rp[1], ddp = rp[2];
     const double vq = rq[0], aq_old = rq[1], ddq = rq[2], Rq = rq[3];
     const double dd = fwd ? ddp : ddq;   // chord between p and q is stored at the lower sample
+#if defined(__CUDA_ARCH__)
+    return eval_core_ilp(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);   // same bits, chains overlapped
+#else
     return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gsb_at(A, q), lat0);
+#endif
 }
 
 // Commits an outcome: state write, memo invalidation, the edge's own memo.  Returns true when the front stops.
@@ -508,7 +587,11 @@ STO_HD void memo_forward_sweep0(const QssArgs& A, const MemoWork& W, const MemoC
                 const double* rn = rec + 4 * (size_t)(q + 1);
                 nv = rn[0]; na = rn[1]; nd = rn[2]; nR = rn[3];
             }
+#if defined(__CUDA_ARCH__)
+            const EvalRes r = eval_core_ilp(V, true, vp, ap, vq, aq_old, ddp, Rq, gsb_at(A, q), lat0);
+#else
             const EvalRes r = eval_core(V, true, vp, ap, vq, aq_old, ddp, Rq, gsb_at(A, q), lat0);
+#endif
 #if defined(STO_HOSTSIM_COUNTERS)
             if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(i0 + t); g_log.push_back(r.kind); }
 #endif

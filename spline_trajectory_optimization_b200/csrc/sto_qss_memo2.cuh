@@ -40,6 +40,11 @@ struct SPlanes {
     __device__ __forceinline__ u64 word(int k, int w) const { return at(k, w); }
     __device__ __forceinline__ void set_word(int k, int w, u64 x) const { at(k, w) = x; }
     __device__ __forceinline__ bool test(int k, int p) const { return (at(k, p >> 6) >> (p & 63)) & 1ull; }
+    // clears bits {a, a1} of one plane: one read-modify-write when both fall into the same word
+    __device__ __forceinline__ void clear_pair(int k, int a, int a1) const {
+        if ((a >> 6) == (a1 >> 6)) at(k, a >> 6) &= ~((1ull << (a & 63)) | (1ull << (a1 & 63)));
+        else { at(k, a >> 6) &= ~(1ull << (a & 63)); at(k, a1 >> 6) &= ~(1ull << (a1 & 63)); }
+    }
     __device__ __forceinline__ void atom_set(int k, int pos) const {
         atomicOr(reinterpret_cast<unsigned*>(&at(k, pos >> 6)) + ((pos >> 5) & 1), 1u << (pos & 31));
     }
@@ -66,78 +71,6 @@ struct SPlanes {
 // the list prefetch ring of sto_qss_memo.cuh's kernels (2 KB per warp >= 8 NW cpw bytes for NW <= 64, cpw <= 4).
 enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5, PL_BLK = 6 };
 
-// The front step with its independent sub-chains free to overlap.  eval_core (sto_qss_memo.cuh) is three divisions and
-// five square roots that nvcc expands into fast path + guarded call to a slow path each: no two of them overlap in one
-// warp, ~1,500 cycles of dependent latency per evaluation on the critical path of every round.  Here the SAME operations
-// in the SAME order per value (every result is bit-identical) are written with the flagged branch-free division / square
-// root of sto_common.cuh (identical bits while the operand-range flag is down; sto_selftest_fp64), so the compiler sees one
-// basic block in which  dd / v -> jerk window -> state speeds,  friction ellipse -> curve speed,  the two table look-ups
-// and the re-initialisation speed  run side by side (~500 cycles of dependent latency).  Anything unusual - a raised flag
-// (zero / infinite / denormal / NaN operand), v_p == 0 - is redone out of line with the plain operators.
-__device__ __noinline__ EvalRes eval_core_plain(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
-                                                double aq_old, double dd, double Rq, double gq, double lat0) {
-    return eval_core(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
-}
-__device__ __forceinline__ EvalRes eval_core_ilp(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq,
-                                                 double aq_old, double dd, double Rq, double gq, double lat0,
-                                                 long long* slow_cnt = nullptr) {
-    // general speed tables (more than three rows: a data-dependent interval search) take the plain path; the reference's
-    // own 3-row tables - everywhere in its tests and examples - are one compare (ppoly4's n == 2 case)
-    if ((V.n_acc != 3) | (V.n_dcc != 3)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
-    bool slow = false;
-    const double dt = div_fast(dd, vp, slow);                                     // front_step_rt: dt = dd / vp
-    const double l = np_clip(ap, V.max_lon_dcc, V.max_lon_acc);                   // max_lat_acc(V, ap)
-    const double Lx = (l > 0.0) ? V.max_lon_acc : V.max_lon_dcc;
-    const double ell = V.max_left_acc * sqrt_fast(1.0 - div_fast(l * l, Lx * Lx, slow), slow);
-    const double mc = sqrt_fast(fabs(fabs(ell) - gq) * Rq, slow);                 // calc_v(max_lat_acc, Rq, gq)
-    const double vinit = sqrt_fast(fabs(fabs(lat0) - gq) * Rq, slow);             // init_speed's calc_v (used on a re-spawn)
-    double vacc, vdcc;
-    {   // ppoly4 for a 3-row table, straight line (a NaN speed raises `slow` in the division above and is redone)
-        const int ia = (vp >= V.acc_x[1]) ? 1 : 0, id = (vp >= V.dcc_x[1]) ? 1 : 0;
-        const double sa = vp - V.acc_x[ia], sd = vp - V.dcc_x[id];
-        double ra = 0.0, za = 1.0, rd = 0.0, zd = 1.0;
-        ra = ra + V.acc_c[3][ia] * za;  za *= sa;
-        rd = rd + V.dcc_c[3][id] * zd;  zd *= sd;
-        ra = ra + V.acc_c[2][ia] * za;  za *= sa;
-        rd = rd + V.dcc_c[2][id] * zd;  zd *= sd;
-        ra = ra + V.acc_c[1][ia] * za;  za *= sa;
-        rd = rd + V.dcc_c[1][id] * zd;  zd *= sd;
-        ra = ra + V.acc_c[0][ia] * za;
-        rd = rd + V.dcc_c[0][id] * zd;
-        vacc = ra; vdcc = rd;
-    }
-    const double md = dt * V.max_jerk;
-    double hi = ap + md, lo = ap - md;
-    hi = np_clip(hi, vdcc, vacc);
-    lo = np_clip(lo, vdcc, vacc);
-    const double vp2 = vp * vp;
-    const double th = 2 * hi * dd, tl = 2 * lo * dd;
-    const double s_hi = sqrt_fast(py_max(fwd ? th + vp2 : vp2 - th, 0.0), slow);
-    const double s_lo = sqrt_fast(py_max(fwd ? tl + vp2 : vp2 - tl, 0.0), slow);
-    const double smax = fwd ? s_hi : s_lo, smin = fwd ? s_lo : s_hi;
-    const double g = py_min3(smax, mc, V.max_speed);
-    const bool respawn = (g > mc) || (g < smin);
-    const bool valid = smin <= g && g <= smax && 0.0 <= g && g <= mc && g <= V.max_speed;
-    const double gg = g * g;
-    const double aq = div_fast(fwd ? gg - vp2 : vp2 - gg, 2 * dd, slow);
-#if defined(STO_PHASE_CLOCKS)
-    if (slow_cnt && (slow | (vp == 0.0))) *slow_cnt += 1;
-#endif
-    if (slow | (vp == 0.0)) return eval_core_plain(V, fwd, vp, ap, vq, aq_old, dd, Rq, gq, lat0);
-    EvalRes r;
-    r.v_new = 0.0; r.a_new = 0.0;
-    if (valid) {
-        if (vq < g) { r.kind = EV_STOP; return r; }
-        r.v_new = g; r.a_new = aq;
-        r.kind = (!same_bits(vq, g) || !same_bits(aq_old, aq)) ? EV_WRITE : EV_KEEP;
-        return r;
-    }
-    if (fwd || !respawn) { r.kind = EV_STOP; return r; }
-    const double vi = (V.max_speed < vinit) ? V.max_speed : vinit;
-    r.v_new = vi;
-    r.kind = (!same_bits(vq, vi) || !same_bits(aq_old, 0.0)) ? EV_SPAWN : EV_RESPAWN;
-    return r;
-}
 __device__ __forceinline__ EvalRes eval_pure_ilp(const QssArgs& A, const sto_vehicle_f64& V, const double* rec, bool fwd,
                                                  int p, int q, double lat0, long long* load_clk = nullptr) {
     const double* rp = rec + 4 * (size_t)p;     // both 32-byte records are fetched up front: one overlapped round trip
@@ -521,7 +454,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         break;
                     }
                 }
-                committer = has && g == 0;
+                committer = has;
             } else {
                 // forward re-spawned list, walked G entries per step: lane (r + k) mod G holds entry r + k
                 int ivf = 0;
@@ -605,46 +538,79 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             const bool spawn = has && (res.kind == EV_SPAWN || res.kind == EV_RESPAWN);
             const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
             const int co = PL_CONT0 + d, so = PL_STOP0 + d;
-            if (committer) {
-                if (changed) {
+            unsigned stop_b = 0, chg_b = 0;
+            if (phase < 2) {
+                // batch phases: every lane commits its own front
+                if (committer) {
+                    if (changed) {
+                        double* rq = rec + 4 * (size_t)q;
+                        rq[0] = res.v_new;
+                        rq[1] = res.a_new;
+                    }
+                    if (res.kind == EV_WRITE || res.kind == EV_KEEP) { P.atom_set(co, p); P.atom_clear(so, p); }
+                    else if (res.kind == EV_STOP) { P.atom_set(so, p); P.atom_clear(co, p); }
+                    else if (res.kind == EV_SPAWN) { P.atom_clear(co, p); P.atom_clear(so, p); }
+                    if (stopped) {
+                        if (phase == 0) P.atom_clear(PL_LIVE0, 64 * w + slot);
+                        else list[slot] = -1;                    // tombstone: the next walk drops it
+                    }
+                }
+                __syncwarp();
+                if (committer && changed) {   // memo_invalidate(q) minus this front's own edge (bit p of the backward planes)
+                    const int qp = (q == 0) ? N - 1 : q - 1;
+                    P.atom_clear(PL_CONT0, q);                                        // edge q -> q-1
+                    P.atom_clear(PL_STOP0, q);
+                    P.atom_clear(PL_CONT1, q);                                        // edge q -> q+1
+                    P.atom_clear(PL_STOP1, q);
+                    P.atom_clear(PL_CONT1, qp);                                       // edge q-1 -> q   (own: q+1 -> q)
+                    P.atom_clear(PL_STOP1, qp);
+                }
+                // bookkeeping, mirrored on every lane of the group
+                stop_b = (__ballot_sync(full, stopped) >> lane0) & gbits;
+                chg_b = (__ballot_sync(full, changed) >> lane0) & gbits;
+                const unsigned spawn_b = (__ballot_sync(full, spawn) >> lane0) & gbits;
+                const unsigned zero_b = (__ballot_sync(full, has && res.kind == EV_ZERO) >> lane0) & gbits;
+                bool ovf = false;
+                if (spawn) {               // a new row at q: it first acts in the next iteration (simulator.py:238-254,351-352)
+                    const int at_ = nB + nnew + __popc(spawn_b & ((1u << g) - 1u));
+                    if (at_ >= A.cap) ovf = true;
+                    else { int iv = q + s + 1; if (iv >= N) iv -= N; LB[at_] = iv; }
+                }
+                const unsigned ovf_b = (__ballot_sync(full, ovf) >> lane0) & gbits;
+                nnew += __popc(spawn_b);
+                if (zero_b) status |= STO_CAND_ZERO_SPEED;
+                if (ovf_b) status |= STO_CAND_ROW_OVERFLOW;
+            } else if (has) {
+                // single phases (forward): every lane of the group holds the same outcome and applies it redundantly with
+                // plain read-modify-writes (same address, same value from every lane; no votes, no atomics); a forward step
+                // never re-spawns (simulator.py:340 cannot hold)
+                stop_b = stopped ? 1u : 0u;
+                chg_b = changed ? 1u : 0u;
+                if (res.kind == EV_ZERO) status |= STO_CAND_ZERO_SPEED;
+                if (res.kind == EV_WRITE) {
                     double* rq = rec + 4 * (size_t)q;
                     rq[0] = res.v_new;
                     rq[1] = res.a_new;
+                    // memo_invalidate(q) + "own edge p -> q is CONT" in four read-modify-writes (memo_invalidate_cont)
+                    const int qn = (q + 1 == N) ? 0 : q + 1;
+                    if ((p >> 6) == (q >> 6)) {
+                        u64& wd = P.at(PL_CONT1, p >> 6);
+                        wd = (wd & ~(1ull << (q & 63))) | (1ull << (p & 63));
+                    } else {
+                        P.at(PL_CONT1, q >> 6) &= ~(1ull << (q & 63));
+                        P.at(PL_CONT1, p >> 6) |= 1ull << (p & 63);
+                    }
+                    P.clear_pair(PL_STOP1, p, q);
+                    P.clear_pair(PL_CONT0, q, qn);
+                    P.clear_pair(PL_STOP0, q, qn);
+                } else if (res.kind == EV_KEEP) {
+                    P.at(PL_CONT1, p >> 6) |= 1ull << (p & 63);
+                    P.at(PL_STOP1, p >> 6) &= ~(1ull << (p & 63));
+                } else if (res.kind == EV_STOP) {
+                    P.at(PL_STOP1, p >> 6) |= 1ull << (p & 63);
+                    P.at(PL_CONT1, p >> 6) &= ~(1ull << (p & 63));
                 }
-                if (res.kind == EV_WRITE || res.kind == EV_KEEP) { P.atom_set(co, p); P.atom_clear(so, p); }
-                else if (res.kind == EV_STOP) { P.atom_set(so, p); P.atom_clear(co, p); }
-                else if (res.kind == EV_SPAWN) { P.atom_clear(co, p); P.atom_clear(so, p); }
-                if (stopped) {
-                    if (phase == 0) P.atom_clear(PL_LIVE0, 64 * w + slot);
-                    else if (phase == 1) list[slot] = -1;        // tombstone: the next walk drops it
-                }
             }
-            if (phase < 2) __syncwarp();   // single phases: one committing lane per group, its atomics stay in program order
-            if (committer && changed) {   // memo_invalidate(q) minus this front's own edge (bit p of its own direction)
-                const int qn = (q + 1 == N) ? 0 : q + 1, qp = (q == 0) ? N - 1 : q - 1;
-                P.atom_clear(PL_CONT0, q);                                            // edge q -> q-1
-                P.atom_clear(PL_STOP0, q);
-                P.atom_clear(PL_CONT1, q);                                            // edge q -> q+1
-                P.atom_clear(PL_STOP1, q);
-                const int e2 = fwd ? qn : qp;      // forward: edge q+1 -> q (own: q-1 -> q); backward: edge q-1 -> q (own: q+1 -> q)
-                P.atom_clear(fwd ? PL_CONT0 : PL_CONT1, e2);
-                P.atom_clear(fwd ? PL_STOP0 : PL_STOP1, e2);
-            }
-            // ---- bookkeeping, mirrored on every lane of the group
-            const unsigned stop_b = (__ballot_sync(full, stopped && committer) >> lane0) & gbits;
-            const unsigned spawn_b = (__ballot_sync(full, spawn && committer) >> lane0) & gbits;
-            const unsigned chg_b = (__ballot_sync(full, changed && committer) >> lane0) & gbits;
-            const unsigned zero_b = (__ballot_sync(full, has && res.kind == EV_ZERO) >> lane0) & gbits;
-            bool ovf = false;
-            if (spawn && committer) {      // a new row at q: it first acts in the next iteration (simulator.py:238-254,351-352)
-                const int at_ = nB + nnew + __popc(spawn_b & ((1u << g) - 1u));
-                if (at_ >= A.cap) ovf = true;
-                else { int iv = q + s + 1; if (iv >= N) iv -= N; LB[at_] = iv; }
-            }
-            const unsigned ovf_b = (__ballot_sync(full, ovf) >> lane0) & gbits;
-            nnew += __popc(spawn_b);
-            if (zero_b) status |= STO_CAND_ZERO_SPEED;
-            if (ovf_b) status |= STO_CAND_ROW_OVERFLOW;
             __syncwarp();
             // ---- post: what the walker does with the outcome
             if (phase == 0) {
