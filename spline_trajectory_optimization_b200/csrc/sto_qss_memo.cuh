@@ -55,16 +55,15 @@ inline MemoWork carve_memo(Alloc alloc, int N, size_t ld, int cap) {
 }
 
 typedef unsigned long long u64;
-#if defined(STO_HOSTSIM_COUNTERS)
-static long long g_memo_evals[2] = {0, 0};   // host-side test instrumentation only
-static long long g_memo_words[2] = {0, 0};
-static long long g_att_hist[2][16] = {};
-static long long g_sp_visits[2] = {0, 0}, g_sp_distinct[2] = {0, 0}, g_sp_on_live_orig[2] = {0, 0};
-static long long g_sp_evals[2] = {0, 0}, g_sp_changed[2] = {0, 0}, g_sp_maxlist[2] = {0, 0};
-static int g_fwd_batch = 0;                    // prototype switch: forward list by memo_spawned_fwd_batch (host analysis only)
-static long long g_fb[4] = {0, 0, 0, 0};       // its batches, committed members, cuts, list entries resolved
-static int g_log_phase = 0, g_log_iter = 0, g_log_on = 0;   // event log: {iteration, sub-pass, sample p, outcome}
-static std::vector<int> g_log;
+// Test-only probes.  tests/hostsim/memo_instrument.h defines these macros (event log, counters, the forward-list
+// batching prototype) before it includes this header; the library build defines none of them and they vanish.
+#ifndef STO_PROBE_EVAL
+#define STO_PROBE_EVAL(fwd)
+#define STO_PROBE_WORD(d, att)
+#define STO_PROBE_EVENT(row_or_sample, kind)
+#define STO_PROBE_LIST_EVAL(d, n, batches)
+#define STO_PROBE_PHASE(k, iters)
+#define STO_PROBE_FWD_LIST(G, A, W, C, V, b, done, s, lat0, nF, steps, status, wF) false
 #endif
 
 STO_HD int ctz64(u64 x) {
@@ -253,9 +252,7 @@ struct EvalRes {
 // radius Rq and gravity term gq.
 STO_HD EvalRes eval_core(const sto_vehicle_f64& V, bool fwd, double vp, double ap, double vq, double aq_old, double dd,
                          double Rq, double gq, double lat0) {
-#if defined(STO_HOSTSIM_COUNTERS)
-    ++g_memo_evals[fwd ? 1 : 0];
-#endif
+    STO_PROBE_EVAL(fwd)
     // (no early exit before the arithmetic: a branch here makes the compiler split the record fetch into two
     //  dependent round trips; with vp == 0 the step below just produces inf/nan that is never stored)
     double g, vp2;
@@ -378,9 +375,7 @@ STO_HD bool apply_res(const QssArgs& A, const MemoCtx& C, int b, bool fwd, int p
     const int N = A.N, d = fwd ? 1 : 0;
     spawn = false;
     changed = false;
-#if defined(STO_HOSTSIM_COUNTERS)
-    if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(p); g_log.push_back(r.kind); }
-#endif
+    STO_PROBE_EVENT(p, r.kind)
     if (r.kind == EV_WRITE) {   // the common changing step: state write, invalidation and own-edge memo fused
         double* rq = A.rec + ((size_t)b * N + (size_t)q) * 4;
         rq[0] = r.v_new;
@@ -484,17 +479,12 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                     } else if (w >= NW) break;
                     L = live.word(w);
                     if (!L) { if (use_mask) words &= ~(1ull << w); else ++w; continue; }
-#if defined(STO_HOSTSIM_COUNTERS)
-                    ++g_memo_words[d];
-#endif
                     steps += popc64(L);
                     start = FWD ? (64 * w + s) : (64 * w - s);  // row i = 64 w + t sits at sample (i -/+ s) mod N
                     if (start >= N) start -= N;
                     if (start < 0) start += N;
                     att = L & ~cont.window(start);              // fronts that are not on a known-clean edge
-#if defined(STO_HOSTSIM_COUNTERS)
-                    if (att) { int c = popc64(att); ++g_att_hist[d][c > 15 ? 15 : c]; }
-#endif
+                    STO_PROBE_WORD(d, att)
                     donemask = 0;
                     open = true;
                 }
@@ -513,22 +503,6 @@ STO_HD void memo_original_rows(const QssArgs& A, const MemoWork& W, const MemoCt
                 if (stop.test(p)) { L &= ~bit; --nlive; att &= ~donemask; continue; }
                 q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
                 pending = true;
-#if defined(STO_HOSTSIM_COUNTERS)
-                if (g_log_on && FWD) {   // analysis: is this front separated from the previous evaluated one by a dead row?
-                    static int last_row = -1, last_iter = -1;
-                    const int row = 64 * w + t;
-                    int gap = 1;
-                    if (last_iter == g_log_iter && last_row >= 0 && last_row < row) {
-                        gap = 0;
-                        for (int rr = last_row + 1; rr < row; ++rr) {
-                            const bool alive = (rr >> 6) == w ? ((L >> (rr & 63)) & 1ull) : live.test(rr);
-                            if (!alive) { gap = 1; break; }
-                        }
-                    }
-                    g_log.push_back(g_log_iter); g_log.push_back(10 + gap); g_log.push_back(row); g_log.push_back(0);
-                    last_row = row; last_iter = g_log_iter;
-                }
-#endif
                 break;
             }
         }
@@ -592,9 +566,7 @@ STO_HD void memo_forward_sweep0(const QssArgs& A, const MemoWork& W, const MemoC
 #else
             const EvalRes r = eval_core(V, true, vp, ap, vq, aq_old, ddp, Rq, gsb_at(A, q), lat0);
 #endif
-#if defined(STO_HOSTSIM_COUNTERS)
-            if (g_log_on) { g_log.push_back(g_log_iter); g_log.push_back(g_log_phase); g_log.push_back(i0 + t); g_log.push_back(r.kind); }
-#endif
+            STO_PROBE_EVENT(i0 + t, r.kind)
             if (r.kind == EV_WRITE || r.kind == EV_KEEP) {
                 contw |= 1ull << t;
                 if (r.kind == EV_WRITE) {
@@ -784,18 +756,6 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
     const Ring cont = C.cont(d), stop = C.stop(d);
     int32_t* list = FWD ? W.spF : W.spB;
     STO_SUBCLK_DECL
-#if defined(STO_HOSTSIM_COUNTERS)
-    if (!skip) {
-        static std::vector<int> seen; seen.assign(N, 0);
-        const Ring live = C.live(d);
-        g_sp_maxlist[d] += nlist;
-        for (int r = 0; r < nlist; ++r) {
-            int iv = list[at(r, ld, b)];
-            ++g_sp_visits[d];
-            if (!seen[iv]) { seen[iv] = 1; ++g_sp_distinct[d]; if (live.test(iv)) ++g_sp_on_live_orig[d]; }
-        }
-    }
-#endif
     if (skip) nlist = 0;
     int r = 0, w = 0, iv = 0, p = 0, q = 0;
     // Prefetch ring: list entries r .. r+RING-1 are copied global -> shared with cp.async (no register dependency,
@@ -842,9 +802,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
             STO_SUBCNT(5)
             bool changed = false, spawn = false;
             const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
-#if defined(STO_HOSTSIM_COUNTERS)
-            ++g_sp_evals[d]; if (changed) ++g_sp_changed[d];
-#endif
+            STO_PROBE_LIST_EVAL(d, 1, changed ? 1 : 0)
             if (spawn) { memo_spawn(A, W, b, q, s, nB, nnew, status); ++nnew; }
             if (!stopped) { if (w != r - 1) list[at(w, ld, b)] = iv; ++w; }
         }
@@ -977,9 +935,7 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
         }
 #endif
         if (!warp_any(cnt > 0)) break;
-#if defined(STO_HOSTSIM_COUNTERS)
-        g_sp_evals[d] += cnt; ++g_sp_changed[d];   // (re-used here: evaluations / batches of the group walker)
-#endif
+        STO_PROBE_LIST_EVAL(d, cnt, 1)   // evaluations / batches of the group walker
 #if defined(__CUDA_ARCH__)
         const int p = my_p, slot = my_slot;
         const bool has = g < cnt;
@@ -1267,78 +1223,6 @@ STO_D void qss_finish_group(const QssArgs& A, double* rec, int b, bool active, i
 }
 #endif
 
-#if defined(STO_HOSTSIM_COUNTERS)
-// PROTOTYPE (host analysis only, not compiled into the library): the forward re-spawned list with up to G evaluations at a
-// time and NO static conflict rule.  A segment of the list is scanned until G entries need an
-// evaluation (duplicates of a member - same sample - are not members); the members are evaluated against the state as
-// it stands; the segment is then resolved in list order from the memo bits read at the START of the segment plus the
-// members' outcomes, without looking at the planes again - which is what a device version can do 8 entries per round:
-//   * an earlier committed member on the same sample p decides the entry: CONT memo -> kept, STOP memo -> dropped;
-//   * an earlier committed member that WROTE the sample p (its q == p) cleared the entry's memo and changed its source:
-//     the entry needs an evaluation on the new state -> the segment is CUT here (the next segment starts at this entry);
-//   * otherwise the entry is what the start-of-segment memo bits say; a member then commits its speculative result (its
-//     inputs are untouched: the only writer of p or q would have triggered one of the two rules above).
-// tests/test_hostsim.py runs this against the one-at-a-time walk (bit-identical state, list, step count) and reports the
-// evaluations per batch it achieves.
-template <int G>
-inline int memo_spawned_fwd_batch(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
-                                  bool skip, int s, double lat0, int nlist, int64_t& steps, int& status) {
-    const int N = A.N, ld = A.ld;
-    const Ring cont = C.cont(1), stop = C.stop(1);
-    int32_t* list = W.spF;
-    if (skip) nlist = 0;
-    int r = 0, w = 0;
-    std::vector<int> cls;   // start-of-segment class per entry: 0 CONT, 1 STOP, 2 needs evaluation
-    while (r < nlist) {
-        int mi[G], mp[G], mq[G], cnt = 0;
-        EvalRes mres[G];
-        cls.clear();
-        int e = r;
-        while (e < nlist && cnt < G) {   // pass A: snapshot classification, member collection
-            int p = list[at(e, ld, b)] + s;
-            if (p >= N) p -= N;
-            const int c = cont.test(p) ? 0 : (stop.test(p) ? 1 : 2);
-            cls.push_back(c);
-            bool dup = false;
-            for (int k = 0; k < cnt; ++k) dup = dup || mp[k] == p;
-            if (c == 2 && !dup) { mi[cnt] = e; mp[cnt] = p; mq[cnt] = (p + 1 == N) ? 0 : p + 1; ++cnt; }
-            ++e;
-        }
-        const int seg_end = e;
-        for (int k = 0; k < cnt; ++k) mres[k] = eval_pure(A, V, b, true, mp[k], mq[k], lat0);   // pass B: all at once
-        ++g_fb[0];
-        int ncommit = 0;                 // members committed so far in this segment (they are the first ncommit ones)
-        int i = r;
-        for (; i < seg_end; ++i) {       // pass C: resolution in list order, planes not consulted
-            const int iv = list[at(i, ld, b)];
-            int p = iv + s;
-            if (p >= N) p -= N;
-            int c = cls[i - r];
-            bool cut = false;
-            for (int k = 0; k < ncommit; ++k) {          // in commit order: later members override
-                if (mres[k].kind == EV_WRITE && mq[k] == p) { c = 2; cut = true; }
-                if (mp[k] == p) { c = (mres[k].kind == EV_STOP || mres[k].kind == EV_ZERO) ? 1 : 0; cut = false; }
-            }
-            if (cut) break;                              // source rewritten: evaluate in the next segment
-            ++g_fb[3];
-            ++steps;
-            if (c == 0) { if (w != i) list[at(w, ld, b)] = iv; ++w; continue; }
-            if (c == 1) continue;
-            // needs an evaluation: it must be the next uncommitted member
-            if (!(ncommit < cnt && mi[ncommit] == i)) { --steps; --g_fb[3]; break; }   // (a duplicate whose member stopped short)
-            bool spawn = false, changed = false;
-            const bool stopped = apply_res(A, C, b, true, mp[ncommit], mq[ncommit], mres[ncommit], status, spawn, changed);
-            if (mres[ncommit].kind == EV_ZERO) { mres[ncommit].kind = EV_ZERO; }
-            if (!stopped) { if (w != i) list[at(w, ld, b)] = iv; ++w; }
-            ++ncommit;
-            ++g_fb[1];
-        }
-        if (i < seg_end) ++g_fb[2];
-        r = i;
-    }
-    return w;
-}
-#endif
 
 // The schedule, one candidate per lane, the 32 lanes of a warp in lock step over (outer iteration, sub-pass, word).
 template <int G>
@@ -1390,11 +1274,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         if (warp_all(done)) break;
         int nnew = 0;
         STO_CLK(0)
-#if defined(STO_HOSTSIM_COUNTERS)
-#define STO_LOG_PHASE(k) { g_log_phase = (k); g_log_iter = iters; }
-#else
-#define STO_LOG_PHASE(k)
-#endif
+#define STO_LOG_PHASE(k) STO_PROBE_PHASE(k, iters)
         STO_LOG_PHASE(0)
         if (G > 1)
             memo_bwd_rows_group<G>(A, W, C, V, b, done || nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status,
@@ -1429,10 +1309,8 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #else
             // forward re-spawned fronts mostly conflict with their list neighbours (1.6 evaluations per batch measured),
             // so they are evaluated one at a time; a lane group spreads the list WALK over its lanes instead
-#if defined(STO_HOSTSIM_COUNTERS)
-            if (g_fwd_batch && G > 1) wF = memo_spawned_fwd_batch<G>(A, W, C, V, b, done, s, lat0, nF, steps, status);
+            if (STO_PROBE_FWD_LIST(G, A, W, C, V, b, done, s, lat0, nF, steps, status, wF)) {}
             else
-#endif
             wF = (G > 1)
                 ? memo_spawned_rows_vec<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0 STO_SUB_ARG)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);

@@ -2,13 +2,13 @@
 // spline_trajectory_optimization_b200/csrc/*.cuh for the host (g++, -ffp-contract=off) so the schedule logic
 // (row tables, ring windows, memoisation) can be unit-tested in the GPU-less authoring container.  Each
 // candidate runs as a "warp of one".  The product never builds, loads or falls back to this file.
-#define STO_HOSTSIM_COUNTERS 1
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include "memo_instrument.h"   // probes + counters: part 1, before the product headers
 #include "../../spline_trajectory_optimization_b200/csrc/sto_common.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_eval.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_fit.cuh"
@@ -16,6 +16,8 @@
 #include "../../spline_trajectory_optimization_b200/csrc/sto_fit_lsq.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss.cuh"
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss_memo.cuh"
+#define STO_INSTRUMENT_PART2 1
+#include "memo_instrument.h"   // part 2: the forward-list batching prototype (needs the product header's types)
 
 extern "C" {
 
