@@ -75,10 +75,12 @@ def run_qss(x, y, radius, vehicle, B=None, sin_bank=None, impl=_lib.QSS_MEMO, pr
         sb = torch.as_tensor(np.ascontiguousarray(sin_bank, dtype=np.float64)).to(dev)
     with torch.cuda.device(dev):
         nbytes = lib.sto_qss_workspace_bytes(N, B, impl)
-        work = _QSS_WORK.get(dev)
+        # one scratch buffer per (device, stream): calls on different streams never share state arrays or bit planes
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        work = _QSS_WORK.get(key)
         if work is None or work.numel() < nbytes:
-            _QSS_WORK[dev] = None
-            work = _QSS_WORK[dev] = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            _QSS_WORK[key] = None
+            work = _QSS_WORK[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         _lib.check(lib.sto_qss_f64(_ptr(x.contiguous()), _ptr(y.contiguous()), _ptr(radius.contiguous()), _ptr(sb), N,
                                    B, ld, C.byref(veh), impl, _ptr(res["lap"]), _ptr(res["summary"]), C.byref(po),
                                    _ptr(res["status"]), _ptr(work), work.numel(), _stream()))
@@ -137,6 +139,10 @@ def sample_splines(t, k, cx_sm, cy_sm, ts, B=None, want=("x", "y", "yaw", "radiu
 
 
 class BatchedLineEvaluator:
+    """One evaluator = one track, one vehicle, one device and ONE workspace: its calls enqueue on the current stream and
+    share that workspace, so an evaluator belongs to one stream at a time (steps pipelined over several streams use one
+    evaluator per stream, as bench.py does; the host-buffer entry `lap_times_host` is thread-safe on its own)."""
+
     def __init__(self, centre_xy, left_normal_xy, ts, vehicle, bank=None, device=None, impl="memo"):
         """centre_xy, left_normal_xy: [M, 2] host arrays; ts: [N] spline parameters in [0, 1);
         bank: [N] bank angle (rad) per resampled point or None; vehicle: Vehicle."""
@@ -218,6 +224,7 @@ class BatchedLineEvaluator:
     def to_sample_major(self, offsets_cm):
         """[B, M] candidate-major CUDA tensor -> [M, round_up(B, 32)] sample-major (device transpose kernel)."""
         B, M = offsets_cm.shape
+        assert offsets_cm.dtype == torch.float64 and offsets_cm.is_cuda, "offsets must be a CUDA float64 tensor"
         ld = round_up32(B)
         out = torch.zeros((M, ld), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
@@ -249,6 +256,7 @@ class BatchedLineEvaluator:
         """Periodic cubic fit.  offsets_sm [M, ld] or points_sm = (px, py) each [M, ld].  Returns u[M+1, ld],
         cx[M+3, ld], cy[M+3, ld], status[ld]."""
         src = offsets_sm if offsets_sm is not None else points_sm[0]
+        assert src.dtype == torch.float64 and src.is_contiguous(), "sample-major float64 input expected"
         M, ld = src.shape
         B = ld if B is None else int(B)
         dev = self.device

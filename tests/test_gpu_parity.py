@@ -417,6 +417,31 @@ def test_fused_banked_oval(sto):
     assert (lap0.cpu().numpy() < laps["memo"]).all()
 
 
+def test_banked_oval_of_the_baseline_config(sto):
+    """BASELINE configs[3] / SURVEY.md 8(d): two 800 m straights + two R = 250 m semicircles, width 15 m, bank 0 -> 9 deg
+    blended over 100 m, M = N at 2 m (the track bench.py --config 3 runs): 96 candidates, bit-exact against the oracle."""
+    import bench
+    from spline_trajectory_optimization_b200 import candidates
+    from spline_trajectory_optimization_b200.models.vehicle import Vehicle
+    rt = bench.build_track(2.0, "oval")
+    M = len(rt.center_d)
+    assert 1500 < M < 1700
+    bank = bench.track_bank(rt)
+    assert bank is not None and abs(np.rad2deg(bank.max()) - 9.0) < 0.2 and bank.min() >= 0.0
+    B = 96
+    off = candidates.smooth_offsets(M, B, rt.dist_to_left, rt.dist_to_right, seed=9)
+    assert np.abs(off).max() > 3.0                                # the 15 m track leaves +-6.5 m
+    nrm = rt.left_normals()
+    ev = sto.BatchedLineEvaluator(rt.center_d[:, :2], nrm, rt.center_d.ts(), Vehicle(test_vehicle_params()), bank=bank)
+    lap, st = ev.lap_times(to_sm(off), B=B)
+    assert not st.cpu().numpy().any()
+    g = golden("cand_m579_n579")
+    ov = O.make_vehicle(*veh_args(g))
+    olap, ost = O.lap_batch(rt.center_d[:, 0], rt.center_d[:, 1], nrm[:, 0], nrm[:, 1], off, rt.center_d.ts(),
+                            np.sin(bank), ov, n_threads=8, ref_pow=0)
+    assert not ost.any() and np.array_equal(lap.cpu().numpy(), olap)
+
+
 def test_long_track_quarter_metre(sto):
     """BASELINE config 5 geometry (Monza at 0.25 m: M = N = 23,160; ~25 M front steps per line in the reference): four
     candidates through the fused path, bit-exact against the oracle.  Exercises multi-word rings (362 words), the
