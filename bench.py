@@ -335,7 +335,9 @@ def fast_mode_leg(ev, d_small, B, exact_lap, rt, peak, big=131072):
     ach_full = alg_full * BL / (ms_lf * 1e-3) / 1e9
     out["roofline"] = {"bound": "hbm", "kernel": "fast_kernel", "peak": peak, "unit": "GB/s",
                        "achieved": ach_full, "frac": ach_full / peak, "counted_on": "full outputs, batch %d" % BL,
-                       "achieved_lap_only": ach_lap, "frac_lap_only": ach_lap / peak, "traffic": None,
+                       "achieved_lap_only": ach_lap, "frac_lap_only": ach_lap / peak,
+                       "traffic": ncu_traffic("fast_kernel")[0], "traffic_source": ncu_traffic("fast_kernel")[1]
+                       + " (full outputs, 131,072 candidates per launch)",
                        "note": "lap-only the path is ~70 flop per algorithmic byte (FP64-pipe side of the 5.7 flop/B "
                                "balance point); with the outputs materialised ~6 flop/B"}
     out["table_staging"] = {"how": "cp.async.bulk (UBLKCP) + mbarrier, six tables once per CTA into shared memory",
@@ -607,7 +609,7 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peaks()
     alg_bytes = (8 * M + 8) * B                      # offsets in, lap out, per candidate (this rank's launch set)
     achieved = alg_bytes / (qss_ms * 1e-3) / 1e9
-    qss_kernel = "qss_%s_kernel" % args.qss
+    qss_kernel = lib.sto_last_qss_kernel().decode() or ("qss_%s_kernel" % args.qss)   # the kernel the launches above used
     traffic, traffic_src = ncu_traffic(qss_kernel) if (cfg == 1 and B == CANDIDATES_PER_GPU) else (None, "captured at config 1 only")
 
     if rank != 0:

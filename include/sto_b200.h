@@ -86,6 +86,7 @@ typedef struct sto_profile_out_f64 {
 /* ---- library ----------------------------------------------------------------------------------- */
 int sto_abi_version(void);
 const char* sto_last_error(void);     /* thread-local text of the last failure */
+const char* sto_last_qss_kernel(void); /* name of the QSS kernel the last launch of this thread used (reports, profiles) */
 int sto_device_count(void);           /* number of sm_100-class devices visible */
 int sto_release(void);                /* frees the per-device arenas / streams cached by the *_host entry points */
 /* Developer tuning overrides, 0 = automatic: "fit_split" (lanes per candidate of the fit kernels), "qss_lanes" (candidates

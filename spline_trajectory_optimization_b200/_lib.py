@@ -41,6 +41,7 @@ class StoError(RuntimeError):
 _SIGNATURES = {
     "sto_abi_version": (C.c_int, []),
     "sto_last_error": (C.c_char_p, []),
+    "sto_last_qss_kernel": (C.c_char_p, []),
     "sto_device_count": (C.c_int, []),
     "sto_release": (C.c_int, []),
     "sto_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),

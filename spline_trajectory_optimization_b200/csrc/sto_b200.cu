@@ -23,6 +23,7 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local const char* g_last_qss_kernel = "";   // which QSS kernel the last launch of this thread used (sto_last_qss_kernel)
 
 int fail(int code, const char* what) {
     g_err = what;
@@ -585,6 +586,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         const int warps = (A.B + lanes - 1) / lanes;
         const int block = 64;
         const int grid = (warps * 32 + block - 1) / block;
+        g_last_qss_kernel = "qss_plain_kernel";
         if (owner) qss_plain_kernel<true><<<grid, block, 0, st>>>(A, lanes, *vehicle);
         else qss_plain_kernel<false><<<grid, block, 0, st>>>(A, lanes, *vehicle);
     } else {
@@ -606,8 +608,10 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
             if (mixed && mixed_smem <= kMemoSmemBudget / 4) {
                 STO_CUDA(cudaFuncSetAttribute(qss_memo_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)mixed_smem));
+                g_last_qss_kernel = "qss_memo_mixed_kernel";
                 qss_memo_mixed_kernel<<<warps, 32, mixed_smem, st>>>(A, w.memo, lanes, *vehicle);
             } else {
+                g_last_qss_kernel = "qss_memo_gplanes_kernel";
                 qss_memo_gplanes_kernel<<<warps, 32, 0, st>>>(A, w.memo, lanes, *vehicle);
             }
             STO_CUDA(cudaGetLastError());
@@ -649,6 +653,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         else STO_LAUNCH_MEMO2(GG, 128);                             \
     } while (0)
             const int per_sm = (warps + 147) / 148;
+            g_last_qss_kernel = "qss_memo2_kernel";
             if (G == 32) STO_LAUNCH_MEMO2_G(32);
             else if (G == 16) STO_LAUNCH_MEMO2_G(16);
             else STO_LAUNCH_MEMO2_G(8);
@@ -662,6 +667,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         STO_CUDA(cudaFuncSetAttribute(qss_memo_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         qss_memo_kernel<GG><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
     } while (0)
+        g_last_qss_kernel = "qss_memo_kernel";
         if (G == 32) STO_LAUNCH_MEMO(32);
         else if (G == 16) STO_LAUNCH_MEMO(16);
         else if (G == 8) STO_LAUNCH_MEMO(8);
@@ -680,6 +686,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
 extern "C" {
 
 int sto_abi_version(void) { return STO_B200_ABI_VERSION; }
+const char* sto_last_qss_kernel(void) { return g_last_qss_kernel; }
 const char* sto_last_error(void) { return g_err.c_str(); }
 
 int sto_set_fit_solver(int solver) {
