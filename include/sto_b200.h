@@ -223,8 +223,8 @@ int sto_lap_time_splines_f64(const double* t, int nt, int k, const double* cx, c
  * reference's lock-step multi-front schedule is NOT emulated, so laps differ from Simulator.run_simulation's by 0.005 .. 3 s
  * (measured: tests/test_fast_mode.py, bench.py `fast_mode`); use it to rank candidates cheaply, then score the short list with
  * sto_lap_time_f64.  Optional outputs (any pointer may be NULL): coefficients cx, cy [M+3][ld] and the sample columns
- * [N][ld].  stage_tables: -1 = stage the six track tables in shared memory per CTA (bulk copy + mbarrier) when they fit,
- * 0 = never (warp-uniform global loads), 1 = require it.  `work` needs sto_fast_workspace_bytes(M, N, B).
+ * [N][ld].  stage_tables: -1 = stage the six track tables in shared memory per CTA (bulk copy + mbarrier) when they fit
+ * and the batch is a single wave of CTAs, 0 = never (warp-uniform global loads), 1 = whenever they fit (error if not).  `work` needs sto_fast_workspace_bytes(M, N, B).
  */
 typedef struct sto_fast_out_f64 {
     double *cx, *cy;                                        /* [M+3][ld] */

@@ -197,7 +197,8 @@ class BatchedLineEvaluator:
         """FAST MODE (separately reported, NOT the reference's result): fit + sampler + a two-sweep QSS with the
         reference's step operator + fill_time in ONE kernel (sto_lap_time_fast_f64, csrc/sto_fast.cuh).  Laps differ from
         `lap_times` (the exact schedule) by 0.005 .. 3 s: use it to rank candidates, then score the short list exactly.
-        outputs=True also materialises cx, cy [M+3, ld] and x, y, yaw, radius, speed, lon_acc, lat_acc, time [N, ld].
+        outputs=True also materialises cx, cy [M+3, ld] and x, y, yaw, radius, speed, lon_acc, lat_acc, time [N, ld]
+        (outputs=<dict returned by an earlier call> reuses those buffers).
         Returns (lap[B], status[B]) or (lap, status, dict of outputs)."""
         M, ld = offsets_sm.shape
         B = ld if B is None else int(B)
@@ -207,10 +208,14 @@ class BatchedLineEvaluator:
             lap = out if out is not None else torch.empty(ld, dtype=torch.float64, device=self.device)
             st = status if status is not None else torch.empty(ld, dtype=torch.int32, device=self.device)
             res, fo = None, None
-            if outputs:
+            if isinstance(outputs, dict):
+                res = outputs
+                assert all(v.shape[1] == ld and v.dtype == torch.float64 for v in res.values())
+            elif outputs:
                 res = {k: torch.empty((M + 3, ld), dtype=torch.float64, device=self.device) for k in ("cx", "cy")}
                 res.update({k: torch.empty((self.N, ld), dtype=torch.float64, device=self.device)
                             for k in ("x", "y", "yaw", "radius", "speed", "lon_acc", "lat_acc", "time")})
+            if res is not None:
                 fo = _lib.StoFastOut(**{k: v.data_ptr() for k, v in res.items()})
             nbytes = self.lib.sto_fast_workspace_bytes(self.M, self.N, B)
             work = self._workspace(nbytes)

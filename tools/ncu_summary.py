@@ -31,7 +31,12 @@ KEYS = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), (
 
 
 def rows_of(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: a .ncu-rep, or the `ncu -i x.ncu-rep --page raw --csv` export of one (taken on the GPU box when the report
+    itself is too large to bring back)."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(out)))
     hdr, units = r[0], r[1]
     return hdr, units, r[2:]

@@ -17,7 +17,7 @@ for name in ("sim_s30k5_i10", "sim_s10k3_i2", "sim_s30k5_i1"):
     sim = Simulator(Vehicle(test_vehicle_params()))
     sim.run_simulation(traj)
     t0 = time.perf_counter(); res = sim.run_simulation(traj); dt = time.perf_counter() - t0
-    print(f"{name}: N={n} run_simulation (plain kernel, owner flags) {dt*1e3:.1f} ms  lap {res.lap_time:.9f} (reference took {float(d['ref_run_time']):.1f} s)")
+    print(f"{name}: N={n} run_simulation (default: memoised kernel) {dt*1e3:.1f} ms  lap {res.lap_time:.9f} (reference took {float(d['ref_run_time']):.1f} s)")
     dev = torch.device("cuda")
     col = lambda a: torch.zeros((n, 32), dtype=torch.float64, device=dev).index_put_((torch.arange(n, device=dev), torch.zeros(n, dtype=torch.long, device=dev)), torch.from_numpy(np.ascontiguousarray(a)).to(dev))
     x, y, r = col(d["in_X"]), col(d["in_Y"]), col(d["in_CURVATURE"])
