@@ -724,6 +724,28 @@ def run_gpu_arm(args):
                                "note": "262,144 / 8 candidates in one launch; bit planes move to global memory at this "
                                        "size (DESIGN.md section 2)"}
         del d_l
+    if args.large_batch and world == 1 and cfg == 1:
+        # ---- informational: BASELINE configs[2] (262,144 candidates) on ONE GPU, the strong-scaling reference of the
+        # multi-GPU lines (bench.py --gpus N runs that configuration sharded): two launches of 131,072
+        tot2, ch2 = WORKLOADS[2]["total"], 131072
+        t_ms = 0.0
+        ok2 = True
+        for rep in range(2):                       # first pass warms up
+            t_ms = 0.0
+            for c0 in range(0, tot2, ch2):
+                d_c = candidates.smooth_offsets_device(M, c0, c0 + ch2, rt.dist_to_left, rt.dist_to_right, dev, seed=1234)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                l_c, s_c = ev.lap_times(d_c, B=ch2)
+                a1.record()
+                torch.cuda.synchronize()
+                t_ms += a0.elapsed_time(a1)
+                ok2 = ok2 and bool((s_c == 0).all().item())
+                del d_c
+        line["config2_on_one_gpu"] = {"candidates": tot2, "launches": tot2 // ch2, "ms": t_ms, "value": tot2 / (t_ms * 1e-3),
+                                      "unit": UNIT, "all_status_ok": ok2,
+                                      "note": "the workload `bench.py --gpus N` (N > 1) shards; device time of the launches only"}
     if world == 1 and cfg == 1 and not args.no_fast_mode:
         line["fast_mode"] = fast_mode_leg(ev, d_off[0][0], B, lap_host, rt, peak)
     if not args.no_cpu_baseline and world == 1:
