@@ -720,6 +720,29 @@ def test_host_entry_is_thread_safe_and_overlaps(sto):
         assert np.array_equal(got[k][0], want[k][0]) and not got[k][1].any(), k
 
 
+def test_device_argmin_pair_kernels(sto):
+    """sharding.DeviceArgmin (sto_argmin_pair_f64 + sto_argmin_pairs_f64; one rank here - the gathered-pairs kernel is
+    also fed four hand-made rank pairs): NaN laps and failed candidates ignored, ties to the lowest global index, an
+    all-invalid shard gives (NaN, -1)."""
+    import ctypes as C
+    from spline_trajectory_optimization_b200 import _lib, sharding
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    red = sharding.DeviceArgmin(dev)
+    lap = torch.tensor([105.5, float("nan"), 104.25, 104.25, 103.0, 110.0], dtype=torch.float64, device=dev)
+    st = torch.tensor([0, 0, 0, 0, 4, 0], dtype=torch.int32, device=dev)        # candidate 4 failed: not eligible
+    best, idx = red(lap, st, 1000)
+    assert float(best[0]) == 104.25 and int(idx[0]) == 1002
+    best, idx = red(torch.full((5,), float("nan"), dtype=torch.float64, device=dev), None, 7)
+    assert np.isnan(float(best[0])) and int(idx[0]) == -1
+    pairs = torch.tensor([107.0, 12.0, float("nan"), -1.0, 106.5, 4100.0, 106.5, 300.0], dtype=torch.float64, device=dev)
+    ob, oi = torch.empty(1, dtype=torch.float64, device=dev), torch.empty(1, dtype=torch.int64, device=dev)
+    _lib.check(lib.sto_argmin_pairs_f64(C.c_void_p(pairs.data_ptr()), 4, C.c_void_p(ob.data_ptr()),
+                                        C.c_void_p(oi.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert float(ob[0]) == 106.5 and int(oi[0]) == 300
+
+
 def test_control_point_variants_batched(sto):
     """§8 f-2 (optimiser-loop batching): the reference's edit -> wrap -> sample_along(ts) -> run_simulation sequence for
     six control-point variants of the s=30,k=5 Monza line, scored in one launch."""
