@@ -641,6 +641,7 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         const size_t smem = sto::memo_smem_bytes(A.N, cpw);
         const int which = g_tune.qss_kernel.load();
         if (which != 1 && w.memo.W <= 64 && G >= 8) {   // the one-loop kernel: lane groups of 8 / 16 / 32, N <= 4096
+            const size_t smem = (size_t)7 * w.memo.W * sizeof(unsigned long long) * cpw;   // six planes + the BLOCKED plane
 #define STO_LAUNCH_MEMO2(GG, MB)                                                                                          \
     do {                                                                                                                  \
         STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -67,8 +67,8 @@ struct SPlanes {
         return lo | (read64(k, 0) << avail);
     }
 };
-// PL_BLK: scratch plane of the backward list's batch collection ("one sample below a pending member"), kept in what was
-// the list prefetch ring of sto_qss_memo.cuh's kernels (2 KB per warp >= 8 NW cpw bytes for NW <= 64, cpw <= 4).
+// PL_BLK: scratch plane of the backward list's batch collection ("one sample below a pending member"); the launch sizes
+// the shared memory for seven planes.
 enum { PL_LIVE0 = 0, PL_LIVE1 = 1, PL_CONT0 = 2, PL_CONT1 = 3, PL_STOP0 = 4, PL_STOP1 = 5, PL_BLK = 6 };
 
 __device__ __forceinline__ EvalRes eval_pure_ilp(const QssArgs& A, const sto_vehicle_f64& V, const double* rec, bool fwd,
