@@ -18,6 +18,7 @@
 #include "../../spline_trajectory_optimization_b200/csrc/sto_qss_memo.cuh"
 #define STO_INSTRUMENT_PART2 1
 #include "memo_instrument.h"   // part 2: the forward-list batching prototype (needs the product header's types)
+#include "memo3_proto.h"       // semantic model of the merged-planes schedule (analysis / test only)
 
 extern "C" {
 
@@ -139,6 +140,8 @@ int hostsim_qss(int impl, const double* x, const double* y, const double* radius
         // impl 1: one lane per candidate; impl 100 + G: emulated groups of G lanes (backward rows G at a time)
         for (int b = 0; b < B; ++b) {
             switch (impl) {
+                case 300: sto::qss_memo3_proto(A, *V, b); break;
+                case 301: sto::qss_memo_q_proto(A, W, C, *V, b); break;
                 case 102: sto::qss_memo_candidate<2>(A, W, C, *V, b, true, 0, 0); break;
                 case 104: sto::qss_memo_candidate<4>(A, W, C, *V, b, true, 0, 0); break;
                 case 108: sto::qss_memo_candidate<8>(A, W, C, *V, b, true, 0, 0); break;
@@ -195,6 +198,23 @@ void hostsim_att_hist(long long* out32) {
 void hostsim_fwd_batch(int on) { sto::g_fwd_batch = on; }
 void hostsim_fwd_batch_counters(long long* out4, int reset) {
     for (int k = 0; k < 4; ++k) { out4[k] = sto::g_fb[k]; if (reset) sto::g_fb[k] = 0; }
+}
+
+void hostsim_m3_stats(long long* out9, int reset) {
+    out9[0] = sto::g_m3.rounds[0]; out9[1] = sto::g_m3.rounds[1]; out9[2] = sto::g_m3.rounds_g8[0];
+    out9[3] = sto::g_m3.rounds_g8[1]; out9[4] = sto::g_m3.evals[0]; out9[5] = sto::g_m3.evals[1];
+    out9[6] = sto::g_m3.dup_created; out9[7] = sto::g_m3.dup_diverged; out9[8] = sto::g_m3.reborn;
+    if (reset) sto::g_m3 = sto::Memo3Stats();
+}
+
+void hostsim_mq_config(int cap, int lanes, int war) { sto::g_mq_cap = cap; sto::g_mq_lanes = lanes; sto::g_mq_war = war; }
+void hostsim_mq_stats(long long* out14, int reset) {
+    for (int d = 0; d < 2; ++d) {
+        out14[d] = sto::g_mq.eval_rounds[d]; out14[2 + d] = sto::g_mq.idle_rounds[d]; out14[4 + d] = sto::g_mq.evals[d];
+        out14[6 + d] = sto::g_mq.chunks[d]; out14[8 + d] = sto::g_mq.qsum[d]; out14[10 + d] = sto::g_mq.visits[d];
+        out14[12 + d] = sto::g_mq.walks[d];
+    }
+    if (reset) sto::g_mq = sto::MemoQStats();
 }
 
 void hostsim_counters(long long* out4, int reset) {

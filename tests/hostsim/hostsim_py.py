@@ -35,7 +35,7 @@ def make_vehicle(scalars, acc_x, acc_c, dcc_x, dcc_c):
 
 
 def build():
-    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "memo_instrument.h")] + [
+    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "memo_instrument.h"), os.path.join(HERE, "memo3_proto.h")] + [
         os.path.join(HERE, "..", "..", "spline_trajectory_optimization_b200", "csrc", f)
         for f in ("sto_common.cuh", "sto_fast.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):

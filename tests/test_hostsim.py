@@ -364,3 +364,41 @@ def test_qss_nan_inputs_equal_oracle(case):
         for k in ("v", "a"):
             assert np.array_equal(h[k][0], o[k], equal_nan=True), (impl, k)
         assert np.isnan(h["lap"][0]) and np.isnan(o["lap"])
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_out_of_order_list_walk_model_is_exact(lanes):
+    """Host model (tests/hostsim/memo3_proto.h) of the out-of-order walk of the re-spawned lists that the lane-group kernel
+    sto_qss_memo3.cuh implements: a list sub-pass is cut into chunks of <= 32 open entries; an entry is processed once the
+    latest earlier open entry on its own sample and on the sample that writes its source are finished, and it may not
+    commit before the earlier entry whose source it writes unless both go in the same round.  Must equal the oracle bit for
+    bit (state, segment times, lap, step and iteration counts) on the goldens, random tracks, word-boundary sizes and the
+    NaN cases."""
+    from helpers import synthetic_closed_track, nan_cases
+    H.lib().hostsim_mq_config(32, lanes, 1)
+    d = golden("sim_s10k3_i2")
+    ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+    cases = []
+    for name in ("sim_s10k3_i2", "sim_s30k5_i3", "sim_oval_bank12", "sim_s10k3_i5"):
+        g = golden(name)
+        cases.append((g["in_X"], g["in_Y"], g["in_CURVATURE"], np.sin(g["in_BANK"])))
+    for seed in range(10):
+        n = int(np.random.default_rng(900 + seed).integers(128, 1500))
+        cases.append(synthetic_closed_track(3000 + seed, n))
+    for n in (128, 129, 192, 193, 257):
+        idx = np.linspace(0, len(d["in_X"]) - 1, n, endpoint=False).astype(int)
+        cases.append((d["in_X"][idx].copy(), d["in_Y"][idx].copy(), d["in_CURVATURE"][idx].copy(), np.zeros(n)))
+    for x, y, r, sb in cases:
+        o = O.qss(x, y, r, sb, ov, 0)
+        h = H.qss(301, x[None], y[None], r[None], sb, hv)
+        assert h["status"][0] == 0
+        for k in ("v", "a", "lat", "time"):
+            assert np.array_equal(h[k][0], o[k]), k
+        assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1
+    for case, (x, y, r, sb) in nan_cases().items():
+        o = O.qss(x, y, r, sb, ov, 0)
+        h = H.qss(301, x[None], y[None], r[None], sb, hv)
+        assert h["status"][0] == 2, case
+        assert h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1, case
+        for k in ("v", "a"):
+            assert np.array_equal(h[k][0], o[k], equal_nan=True), (case, k)
