@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsto_b200.so")
 SOURCES = ["sto_b200.cu"]
-HEADERS = ["sto_common.cuh", "sto_fast.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh", "sto_qss_memo2.cuh",
+HEADERS = ["sto_common.cuh", "sto_fast.cuh", "sto_fit.cuh", "sto_fit_lsq.cuh", "sto_eval.cuh", "sto_qss.cuh", "sto_qss_memo.cuh", "sto_qss_memo2.cuh", "sto_qss_memo3.cuh",
            os.path.join("..", "..", "include", "sto_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

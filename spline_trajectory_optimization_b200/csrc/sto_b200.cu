@@ -19,6 +19,7 @@
 #include "sto_qss.cuh"
 #include "sto_qss_memo.cuh"
 #include "sto_qss_memo2.cuh"
+#include "sto_qss_memo3.cuh"
 
 namespace {
 
@@ -48,7 +49,9 @@ struct Tuning {
     std::atomic<int> qss_planes{0};   // 1 = bit planes in shared memory, 2 = global (mixed decided by residency),
                                       // 3 = all global, 4 = CONT planes shared + live / STOP planes global
     std::atomic<int> qss_kernel{0};   // small batches: 1 = the four-walker kernel (sto_qss_memo.cuh), 2 = the one-loop kernel
-                                      // (sto_qss_memo2.cuh); 0 = the one-loop kernel wherever it applies (N <= 4096)
+                                      // (sto_qss_memo2.cuh), 3 = the one-loop kernel with the re-spawned lists walked out of
+                                      // order (sto_qss_memo3.cuh), 4 = the one-loop kernel with the forward original-row
+                                      // sub-pass run-parallel; 0 = automatic (N <= 4096: see launch_qss)
     std::atomic<int> fit_solver{STO_FIT_FITPACK};   // sto_set_fit_solver
 };
 Tuning g_tune;
@@ -59,7 +62,7 @@ struct TuningFromEnv {
         if (const char* e = getenv("STO_FIT_SOLVER")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.fit_solver = v; }
         if (const char* e = getenv("STO_QSS_LANES")) { const int v = atoi(e); if (v >= 1 && v <= 32) g_tune.qss_lanes = v; }
         if (const char* e = getenv("STO_QSS_GROUP")) { const int v = atoi(e); if (pow2_le32(v)) g_tune.qss_group = v; }
-        if (const char* e = getenv("STO_QSS_KERNEL")) { const int v = atoi(e); if (v >= 0 && v <= 2) g_tune.qss_kernel = v; }
+        if (const char* e = getenv("STO_QSS_KERNEL")) { const int v = atoi(e); if (v >= 0 && v <= 4) g_tune.qss_kernel = v; }
         if (const char* e = getenv("STO_QSS_PLANES"))
             g_tune.qss_planes = (e[0] == 's') ? 1 : (e[0] != 'g') ? 0 : (e[1] == '\0') ? 2 : (e[1] == '0') ? 3 : 4;
     }
@@ -379,14 +382,25 @@ __global__ void fast_kernel(sto::FastArgs Ain, FastTables T, const __grid_consta
 // The same launch shape with the one-loop kernel (sto_qss_memo2.cuh): shared evaluate-and-commit, four small search stages.
 // MAXR = register budget per thread: 168 leaves the allocation free (~160 registers, at most 12 one-warp CTAs per SM),
 // 144 / 128 cap it for batches that put 13 / more warps on an SM.
-template <int G, int MAXR>
+template <int G, int MAXR, bool FP>
 __global__ void __maxnreg__(MAXR) qss_memo2_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
     const int lane = threadIdx.x & 31, warp = blockIdx.x;
     const int grp = lane / G, g = lane % G;
     const int b = warp * cpw + grp;
     const bool active = grp < cpw && b < A.B;
     const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, nullptr, 0, lane, A.N, W.W);
-    sto::qss_memo2_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G, grp < cpw ? grp : 0, cpw);
+    sto::qss_memo2_candidate<G, FP>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G, grp < cpw ? grp : 0, cpw);
+}
+
+// The one-loop kernel with the re-spawned lists walked out of order (sto_qss_memo3.cuh).
+template <int G, int MAXR>
+__global__ void __maxnreg__(MAXR) qss_memo3_kernel(sto::QssArgs A, sto::MemoWork W, int cpw, const __grid_constant__ sto_vehicle_f64 V) {
+    const int lane = threadIdx.x & 31, warp = blockIdx.x;
+    const int grp = lane / G, g = lane % G;
+    const int b = warp * cpw + grp;
+    const bool active = grp < cpw && b < A.B;
+    const sto::MemoCtx C = sto::memo_bind(sto_planes, cpw, grp < cpw ? grp : 0, nullptr, 0, lane, A.N, W.W);
+    sto::qss_memo3_candidate<G>(A, W, C, V, active ? b : A.B - 1, active, g, grp * G, grp < cpw ? grp : 0, cpw);
 }
 
 // FP64 pipe peak for the roofline report: 8 independent DFMA chains per thread, every SM full.
@@ -640,20 +654,43 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
         const int warps = (A.B + cpw - 1) / cpw;
         const size_t smem = sto::memo_smem_bytes(A.N, cpw);
         const int which = g_tune.qss_kernel.load();
-        if (which != 1 && w.memo.W <= 64 && G >= 8) {   // the one-loop kernel: lane groups of 8 / 16 / 32, N <= 4096
-            const size_t smem = (size_t)7 * w.memo.W * sizeof(unsigned long long) * cpw;   // six planes + the BLOCKED plane
-#define STO_LAUNCH_MEMO2(GG, MB)                                                                                          \
-    do {                                                                                                                  \
-        STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        qss_memo2_kernel<GG, MB><<<warps, 32, smem, st>>>(A, w.memo, cpw, *vehicle);                                      \
+        if (which != 1 && w.memo.W <= 64 && G >= 8) {   // the one-loop kernels: lane groups of 8 / 16 / 32, N <= 4096
+            // default (0, 4): sto_qss_memo2.cuh with the forward original-row sub-pass run-parallel (measured on B200, Monza:
+            // 4,096 lines 30.9 ms against 33.2 ms with the sequential sweep, 8,192 lines 41.1 / 43.2, 2,048 lines 23.9 / 25.7,
+            // 1,024 lines 19.6 / 20.7); 2 = the sequential sweep; 3 = sto_qss_memo3.cuh, the re-spawned lists walked out of
+            // order (fewer rounds, 1,882 instead of 5,244 on the forward list, but the list scan that finds them costs more
+            // than they save: 40.2 ms) - kept selectable for A/B runs, with the 168-register build only
+            const int per_sm = (warps + 147) / 148;
+            const int mb = (per_sm <= 12) ? 168 : (per_sm <= 13) ? 144 : 128;
+            if (which == 3) {
+                const size_t smem3 = sto::memo3_smem_bytes(w.memo.W, cpw);
+#define STO_LAUNCH_MEMO3(GG)                                                                                               \
+    do {                                                                                                                   \
+        STO_CUDA(cudaFuncSetAttribute(qss_memo3_kernel<GG, 168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        qss_memo3_kernel<GG, 168><<<warps, 32, smem3, st>>>(A, w.memo, cpw, *vehicle);                                     \
+    } while (0)
+                g_last_qss_kernel = "qss_memo3_kernel";
+                if (G == 32) STO_LAUNCH_MEMO3(32);
+                else if (G == 16) STO_LAUNCH_MEMO3(16);
+                else STO_LAUNCH_MEMO3(8);
+#undef STO_LAUNCH_MEMO3
+                STO_CUDA(cudaGetLastError());
+                return STO_OK;
+            }
+            // six planes + the BLOCKED plane + the TODO word of the run-parallel forward phase
+            const size_t smem2 = ((size_t)7 * w.memo.W + 1) * sizeof(unsigned long long) * cpw;
+#define STO_LAUNCH_MEMO2(GG, MB, FP)                                                                                            \
+    do {                                                                                                                        \
+        STO_CUDA(cudaFuncSetAttribute(qss_memo2_kernel<GG, MB, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
+        qss_memo2_kernel<GG, MB, FP><<<warps, 32, smem2, st>>>(A, w.memo, cpw, *vehicle);                                       \
     } while (0)
 #define STO_LAUNCH_MEMO2_G(GG)                                      \
     do {                                                            \
-        if (per_sm <= 12) STO_LAUNCH_MEMO2(GG, 168);                \
-        else if (per_sm <= 13) STO_LAUNCH_MEMO2(GG, 144);           \
-        else STO_LAUNCH_MEMO2(GG, 128);                             \
+        if (which == 2) STO_LAUNCH_MEMO2(GG, 168, false);           \
+        else if (mb == 168) STO_LAUNCH_MEMO2(GG, 168, true);        \
+        else if (mb == 144) STO_LAUNCH_MEMO2(GG, 144, true);        \
+        else STO_LAUNCH_MEMO2(GG, 128, true);                       \
     } while (0)
-            const int per_sm = (warps + 147) / 148;
             g_last_qss_kernel = "qss_memo2_kernel";
             if (G == 32) STO_LAUNCH_MEMO2_G(32);
             else if (G == 16) STO_LAUNCH_MEMO2_G(16);
@@ -705,7 +742,7 @@ int sto_set_tuning(const char* key, int value) {
     if (k == "qss_lanes" && value >= 0 && value <= 32) { g_tune.qss_lanes = value; return STO_OK; }
     if (k == "qss_group" && (value == 0 || pow2_le32(value))) { g_tune.qss_group = value; return STO_OK; }
     if (k == "qss_planes" && value >= 0 && value <= 4) { g_tune.qss_planes = value; return STO_OK; }
-    if (k == "qss_kernel" && value >= 0 && value <= 2) { g_tune.qss_kernel = value; return STO_OK; }
+    if (k == "qss_kernel" && value >= 0 && value <= 4) { g_tune.qss_kernel = value; return STO_OK; }
     return fail(STO_ERR_INVALID, "unknown tuning key or value");
 }
 int sto_fit_solver_lanes(int M, int B) {

@@ -821,7 +821,7 @@ STO_HD int memo_spawned_rows(const QssArgs& A, const MemoWork& W, const MemoCtx&
 template <bool FWD, int G>
 STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                                    int b, bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps,
-                                   int& status, int g, int lane0) {
+                                   int& status, int g, int lane0, int& ndead) {
     const int N = A.N, ld = A.ld, d = FWD ? 1 : 0;
     const Ring cont = C.cont(d), stop = C.stop(d);
     int32_t* list = FWD ? W.spF : W.spB;
@@ -979,6 +979,7 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
             const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
             const unsigned spawn_b = (__ballot_sync(0xffffffffu, spawn) >> lane0) & gmask;
             const unsigned zero_b = (__ballot_sync(0xffffffffu, has && res.kind == EV_ZERO) >> lane0) & gmask;
+            ndead += __popc((__ballot_sync(0xffffffffu, stopped) >> lane0) & gmask);   // tombstones left in the list
             int st = 0;
             if (spawn) memo_spawn(A, W, b, q, s, nB, nnew + __popc(spawn_b & ((1u << g) - 1u)), st);
             const unsigned ovf_b = (__ballot_sync(0xffffffffu, st != 0) >> lane0) & gmask;
@@ -1000,7 +1001,7 @@ STO_HD int memo_spawned_rows_group(const QssArgs& A, const MemoWork& W, const Me
             bool spawn, changed;
             const bool stopped = apply_res(A, C, b, FWD, pend_p[k], qq[k], res[k], status, spawn, changed);
             if (spawn) { memo_spawn(A, W, b, qq[k], s, nB, nnew, status); ++nnew; }
-            if (stopped) list[at(pend_slot[k], ld, b)] = -1;
+            if (stopped) { list[at(pend_slot[k], ld, b)] = -1; ++ndead; }
         }
 #endif
         if (status != 0) { nlist = r; held = -2; }   // abandon the walk of a failed candidate
@@ -1266,13 +1267,14 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
 #endif
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
     u64 wordsB = (W.W >= 64) ? ~0ull : ((1ull << W.W) - 1ull), wordsF = wordsB;  // words with running fronts
-    int nB = 0, nF = 0;  // live re-spawned fronts per direction
+    int nB = 0, nF = 0;  // lengths of the re-spawned lists (a front that stops in a batch leaves a tombstone in the backward list)
+    int tombB = 0;       // tombstones in the backward list: nB - tombB fronts are live
     int s = 0, iters = 0;
     int64_t steps = 0;
     for (;;) {
-        const bool done = (nliveB == 0 && nliveF == 0 && nB == 0 && nF == 0) || status != 0;
+        const bool done = (nliveB == 0 && nliveF == 0 && nB - tombB == 0 && nF == 0) || status != 0;
         if (warp_all(done)) break;
-        int nnew = 0;
+        int nnew = 0, deadB = 0, deadF_unused = 0;
         STO_CLK(0)
 #define STO_LOG_PHASE(k) STO_PROBE_PHASE(k, iters)
         STO_LOG_PHASE(0)
@@ -1288,7 +1290,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
         int wB = 0;
         if (warp_any(!done && nB > 0))
             wB = (G > 1)
-                ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0)
+                ? memo_spawned_rows_group<false, G>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status, g, lane0, deadB)
                 : memo_spawned_rows<false>(A, W, C, V, b, done, s, lat0, nB, nB, nnew, steps, status STO_SUB_ARG);  // 0 if done
         STO_CLK(2)
         STO_LOG_PHASE(2)
@@ -1304,7 +1306,7 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             int none = 0;  // rows spawned in this iteration's backward sub-pass wait a turn (simulator.py:351-352)
 #if defined(STO_GROUP_SF)
             wF = (G > 1)
-                ? memo_spawned_rows_group<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0)
+                ? memo_spawned_rows_group<true, G>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status, g, lane0, deadF_unused)
                 : memo_spawned_rows<true>(A, W, C, V, b, done, s, lat0, nF, nB, none, steps, status STO_SUB_ARG);
 #else
             // forward re-spawned fronts mostly conflict with their list neighbours (1.6 evaluations per batch measured),
@@ -1355,10 +1357,12 @@ STO_HD void qss_memo_candidate(const QssArgs& A, const MemoWork& W, const MemoCt
             }
             nB = wB + nnew;
             nF = wF + nnew;
+            tombB = deadB;
             s = (s + 1 == N) ? 0 : s + 1;
             ++iters;
             if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;
         }
+        (void)deadF_unused;
         STO_CLK(5)
     }
     STO_CLK(6)

@@ -161,7 +161,8 @@ __device__ __noinline__ Sweep0Out memo2_sweep0(const QssArgs& A, const sto_vehic
 // test them side by side (a few LDS and shifts each, the same instruction stream for every lane of the warp); the
 // group then ORs its findings.  Returns the mask of words to visit; adds the live fronts to `steps` (every live front
 // takes a step in the reference's schedule), drops words without live fronts from `words`.
-template <int G>
+// STORE_ATT (the parallel forward phase): the attention word of every word that needs a visit is left in the BLOCKED plane.
+template <int G, bool STORE_ATT = false>
 __device__ __forceinline__ u64 memo2_scan_words(const SPlanes& P, bool fwd, bool skip, int s, int g, u64& words,
                                                 int64_t& steps) {
     const unsigned full = 0xffffffffu;
@@ -177,7 +178,11 @@ __device__ __forceinline__ u64 memo2_scan_words(const SPlanes& P, bool fwd, bool
         int start = fwd ? 64 * w0 + s : 64 * w0 - s;
         if (start >= P.N) start -= P.N;
         if (start < 0) start += P.N;
-        if (Lw & ~P.window(plC, start)) need |= 1ull << w0;
+        const u64 a = Lw & ~P.window(plC, start);
+        if (a) {
+            need |= 1ull << w0;
+            if (STORE_ATT) P.set_word(PL_BLK, w0, a);
+        }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -198,11 +203,20 @@ __device__ __forceinline__ u64 memo2_scan_words(const SPlanes& P, bool fwd, bool
 #define STO2_CNT(slot)
 #endif
 
-template <int G>
+// FP: the forward sub-pass over the original rows with independent runs of live rows in parallel.  That sub-pass is a
+// sequential sweep in row order, but a row only ever affects the NEXT row (it writes that row's source sample), and only
+// if that row is live: a dirty front is READY when no dirty front sits below it in its own run of consecutive live rows.
+// Per round the G lowest words with dirty fronts (TODO word, attention words in the BLOCKED plane) each offer their lowest
+// dirty front if it is ready; all are evaluated on the state as it stands and committed together in two phases (fronts of
+// different runs are >= 2 samples apart; rows N-1 and 0 are ordered by the two-phase commit); a state-changing step makes
+// the next live row dirty.  Host model against the oracle: tests/hostsim/memo3_proto.h (memo_forward_rows_par),
+// tests/test_hostsim.py::test_parallel_forward_rows_model_is_exact: 2,537 evaluations in 889 rounds on a Monza line.
+template <int G, bool FP = false>
 __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V,
                                     int b, bool active, int g, int lane0, int col, int cpw) {
     const int N = A.N, ld = A.ld, NW = W.W;
     const SPlanes P{col, cpw, NW, N};
+    u64& Tw = sto_memo2_planes[(size_t)7 * NW * cpw + col];   // FP: words of the forward sub-pass that hold dirty fronts
     const unsigned full = 0xffffffffu;
     const unsigned gbits = (G == 32) ? full : ((1u << G) - 1u);
     const double lat0 = max_lat_acc(V, 0.0);
@@ -245,13 +259,14 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
 #endif
     int nliveB = active ? N : 0, nliveF = active ? N : 0;
     u64 wordsB = (NW >= 64) ? ~0ull : ((1ull << NW) - 1ull), wordsF = wordsB;   // words with running fronts (NW <= 64)
-    int nB = 0, nF = 0;    // live re-spawned fronts per direction
+    int nB = 0, nF = 0;    // lengths of the re-spawned lists (a backward front that stops in a batch leaves a tombstone)
+    int tombB = 0;         // tombstones in the backward list: nB - tombB fronts are live
     int s = 0, iters = 0;  // s = (k - 1) mod N
     int64_t steps = 0;
     for (;;) {
-        const bool done = (nliveB == 0 && nliveF == 0 && nB == 0 && nF == 0) || status != 0;
+        const bool done = (nliveB == 0 && nliveF == 0 && nB - tombB == 0 && nF == 0) || status != 0;
         if (warp_all(done)) break;
-        int nnew = 0, wB = 0, wF = 0;
+        int nnew = 0, wB = 0, wF = 0, deadB = 0;
         // ---- state of the phase in flight (one phase at a time: the variables are shared)
         u64 todo = 0, L = 0, att = 0, bit = 0;   // original rows: words to visit, live word, fronts needing attention
         int w = 0;
@@ -283,8 +298,12 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         nliveF = o.nlive; status = o.status; steps = o.steps;
                     }
                     skip = done || nliveF == 0;
-                    todo = memo2_scan_words<G>(P, true, skip, s, g, wordsF, steps);
+                    todo = memo2_scan_words<G, FP>(P, true, skip, s, g, wordsF, steps);
                     open = false;
+                    if (FP) {
+                        if (g == 0) Tw = todo;
+                        __syncwarp();
+                    }
                 } else {
                     if (!warp_any(!done && nF > 0)) break;
                     list = LF; nlist = done ? 0 : nF; r = 0; wr = 0;
@@ -424,6 +443,56 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 p = has ? my_p : 0;
                 slot = my_slot;
                 committer = has;
+            } else if (FP && phase == 2) {
+                // forward sub-pass over the original rows, independent live runs in parallel: lane g takes the g-th lowest
+                // word with dirty fronts and offers its lowest dirty front if no dirty front sits below it in its run
+                int nk = 0;
+                for (;;) {
+                    const u64 tw = skip ? 0ull : Tw;
+                    if (g < popc64(tw)) {
+                        w = kth_bit(tw, g);
+                        u64 Lm = P.word(PL_LIVE1, w), am = P.word(PL_BLK, w);
+                        const u64 Lm0 = Lm, am0 = am;
+                        for (;;) {
+                            if (!am) break;
+                            const int t = ctz64(am);
+                            const u64 bm = 1ull << t, low = bm - 1ull;
+                            bool blocked = false;
+                            if ((Lm & low) == low) {         // every row below in this word is live: the run goes on below
+                                for (int v = w - 1; v >= 0; --v) {
+                                    const u64 dead = ~P.word(PL_LIVE1, v);       // (rows >= N sit in the last word only)
+                                    const u64 av = P.word(PL_BLK, v);
+                                    if (!dead) { if (av) { blocked = true; break; } continue; }
+                                    const int z = 63 - __clzll((long long)dead);  // highest dead row of the word
+                                    if (z < 63 && (av >> (z + 1))) blocked = true;
+                                    break;
+                                }
+                            }
+                            if (blocked) break;
+                            p = 64 * w + t + s;
+                            if (p >= N) p -= N;
+                            if (P.test(PL_STOP1, p)) { Lm &= ~bm; am &= ~bm; ++nk; continue; }   // a STOP edge: the front dies
+                            has = true;
+                            slot = t;
+                            break;
+                        }
+                        if (Lm != Lm0) P.set_word(PL_LIVE1, w, Lm);
+                        if (am != am0) {
+                            P.set_word(PL_BLK, w, am);
+                            if (!am) P.atom_clear(7, w);     // plane 7, bit w: the TODO word
+                        }
+                    }
+                    __syncwarp();
+                    // nobody in the warp has a front, but fronts died and a word may have become ready: look again
+                    if (warp_any(has) || !warp_any(!skip && Tw != 0ull)) break;
+                }
+                {
+                    int dk = nk;
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) dk += __shfl_xor_sync(full, dk, o);
+                    nliveF -= dk;
+                }
+                committer = has;
             } else if (phase == 2) {
                 // forward sub-pass over the original rows (a sequential sweep): one front per round
                 if (!skip) {
@@ -539,7 +608,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             const bool changed = has && (res.kind == EV_WRITE || res.kind == EV_SPAWN);
             const int co = PL_CONT0 + d, so = PL_STOP0 + d;
             unsigned stop_b = 0, chg_b = 0;
-            if (phase < 2) {
+            if (phase < 2 || (FP && phase == 2)) {
                 // batch phases: every lane commits its own front
                 if (committer) {
                     if (changed) {
@@ -552,18 +621,25 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                     else if (res.kind == EV_SPAWN) { P.atom_clear(co, p); P.atom_clear(so, p); }
                     if (stopped) {
                         if (phase == 0) P.atom_clear(PL_LIVE0, 64 * w + slot);
+                        else if (FP && phase == 2) P.atom_clear(PL_LIVE1, 64 * w + slot);
                         else list[slot] = -1;                    // tombstone: the next walk drops it
                     }
                 }
                 __syncwarp();
-                if (committer && changed) {   // memo_invalidate(q) minus this front's own edge (bit p of the backward planes)
-                    const int qp = (q == 0) ? N - 1 : q - 1;
+                if (committer && changed) {   // memo_invalidate(q) minus this front's own edge
                     P.atom_clear(PL_CONT0, q);                                        // edge q -> q-1
                     P.atom_clear(PL_STOP0, q);
                     P.atom_clear(PL_CONT1, q);                                        // edge q -> q+1
                     P.atom_clear(PL_STOP1, q);
-                    P.atom_clear(PL_CONT1, qp);                                       // edge q-1 -> q   (own: q+1 -> q)
-                    P.atom_clear(PL_STOP1, qp);
+                    if (FP && fwd) {
+                        const int qn = (q + 1 == N) ? 0 : q + 1;
+                        P.atom_clear(PL_CONT0, qn);                                   // edge q+1 -> q   (own: q-1 -> q)
+                        P.atom_clear(PL_STOP0, qn);
+                    } else {
+                        const int qp = (q == 0) ? N - 1 : q - 1;
+                        P.atom_clear(PL_CONT1, qp);                                   // edge q-1 -> q   (own: q+1 -> q)
+                        P.atom_clear(PL_STOP1, qp);
+                    }
                 }
                 // bookkeeping, mirrored on every lane of the group
                 stop_b = (__ballot_sync(full, stopped) >> lane0) & gbits;
@@ -578,6 +654,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 }
                 const unsigned ovf_b = (__ballot_sync(full, ovf) >> lane0) & gbits;
                 nnew += __popc(spawn_b);
+                if (phase == 1) deadB += __popc(stop_b);     // tombstones: live fronts = list length - tombstones
                 if (zero_b) status |= STO_CAND_ZERO_SPEED;
                 if (ovf_b) status |= STO_CAND_ROW_OVERFLOW;
             } else if (has) {
@@ -626,6 +703,21 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
             } else if (phase == 1) {
                 if (has) P.atom_clear(PL_BLK, (p == 0) ? N - 1 : p - 1);   // the batch is committed: nothing is blocked any more
                 if (status != 0) nlist = r;                  // abandon the walk of a failed candidate
+            } else if (FP && phase == 2) {
+                nliveF -= __popc(stop_b);
+                const int row = 64 * w + slot;
+                if (has) {
+                    P.atom_clear(PL_BLK, row);               // this front is done
+                    // the next row reads the sample just written: it faces a dirty edge now if it is live (row N-1's
+                    // successor, row 0, went first in this sub-pass)
+                    if (changed && row + 1 < N && P.test(PL_LIVE1, row + 1)) {
+                        P.atom_set(PL_BLK, row + 1);
+                        if (slot == 63) P.atom_set(7, w + 1);
+                    }
+                }
+                __syncwarp();
+                if (has && P.word(PL_BLK, w) == 0ull) P.atom_clear(7, w);   // (after every mark of the round)
+                __syncwarp();
             } else if (phase == 2) {
                 if (has) {
                     att &= ~bit;
@@ -672,6 +764,7 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
         if (!done) {
             nB = wB + nnew;
             nF = wF + nnew;
+            tombB = deadB;
             s = (s + 1 == N) ? 0 : s + 1;
             ++iters;
             if (iters > 64 * N + 1024) status |= STO_CAND_NO_CONVERGENCE;

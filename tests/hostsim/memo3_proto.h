@@ -171,7 +171,7 @@ inline void qss_memo3_proto(const QssArgs& A, const sto_vehicle_f64& V, int b) {
 struct MemoQStats { long long eval_rounds[2] = {0, 0}, idle_rounds[2] = {0, 0}, evals[2] = {0, 0}, chunks[2] = {0, 0},
                     qsum[2] = {0, 0}, visits[2] = {0, 0}, walks[2] = {0, 0}; };
 static MemoQStats g_mq;
-static int g_mq_cap = 32, g_mq_lanes = 8, g_mq_war = 1;
+static int g_mq_cap = 32, g_mq_lanes = 8, g_mq_war = 1, g_mq_fpar = 0;
 
 template <bool FWD>
 inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
@@ -284,6 +284,92 @@ inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCt
     return w;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Prototype 3 (analysis / test only): the forward sub-pass over the ORIGINAL rows with independent live runs in parallel.
+// The sub-pass is a sequential sweep in row order, but a row only affects the NEXT row, and only if that row is live: a
+// dirty front is READY when no dirty front sits below it in its own run of consecutive live rows.  Per round the G lowest
+// words with dirty fronts offer their lowest dirty front if it is ready; all are evaluated on the state as it stands and
+// committed together; a changing step makes the next live row dirty.
+struct MemoFStats { long long rounds = 0, evals = 0, subpasses = 0; };
+static MemoFStats g_mf;
+
+inline void memo_forward_rows_par(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
+                                  bool skip, int s, double lat0, int& nlive, u64& words, int64_t& steps, int& status) {
+    const int N = A.N, NW = W.W, G = g_mq_lanes;
+    if (skip) return;
+    const Ring live = C.live(1), cont = C.cont(1), stop = C.stop(1);
+    std::vector<u64> att(NW, 0), Lw(NW, 0);
+    u64 todo = 0;
+    for (int w = 0; w < NW; ++w) {
+        if (!((words >> w) & 1ull)) continue;
+        const u64 L = live.word(w);
+        Lw[w] = L;
+        if (!L) { words &= ~(1ull << w); continue; }
+        steps += popc64(L);
+        int start = 64 * w + s;
+        if (start >= N) start -= N;
+        att[w] = L & ~cont.window(start);
+        if (att[w]) todo |= 1ull << w;
+    }
+    ++g_mf.subpasses;
+    while (todo && status == 0) {
+        struct Cd { int w, t, p; };
+        Cd cd[64];
+        int nc = 0;
+        u64 tw = todo;
+        for (int g = 0; g < G && tw; ++g) {
+            const int w = ctz64(tw);
+            tw &= tw - 1ull;
+            for (;;) {
+                if (!att[w]) { todo &= ~(1ull << w); break; }
+                const int t = ctz64(att[w]);
+                const u64 bit = 1ull << t, low = bit - 1ull;
+                bool blocked = false;
+                if ((Lw[w] & low) == low) {           // every row below in this word is live: the run goes on below
+                    for (int v = w - 1; v >= 0; --v) {
+                        const int nbits = (N - 64 * v >= 64) ? 64 : N - 64 * v;
+                        const u64 fullm = (nbits == 64) ? ~0ull : ((1ull << nbits) - 1ull);
+                        const u64 dead = ~Lw[v] & fullm;
+                        if (!dead) { if (att[v]) { blocked = true; break; } continue; }
+                        const int z = 63 - __builtin_clzll(dead);            // highest dead row of the word
+                        if (z < 63 && (att[v] >> (z + 1))) blocked = true;
+                        break;
+                    }
+                }
+                if (blocked) break;
+                int p = 64 * w + t + s;
+                if (p >= N) p -= N;
+                if (stop.test(p)) { Lw[w] &= ~bit; live.set_word(w, Lw[w]); --nlive; att[w] &= ~bit; continue; }
+                cd[nc++] = Cd{w, t, p};
+                break;
+            }
+        }
+        if (!nc) continue;
+        ++g_mf.rounds;
+        g_mf.evals += nc;
+        EvalRes res[64];
+        for (int m = 0; m < nc; ++m) {
+            const int p = cd[m].p, q = (p + 1 == N) ? 0 : p + 1;
+            res[m] = eval_pure(A, V, b, true, p, q, lat0);
+        }
+        for (int m = 0; m < nc; ++m) {
+            const int p = cd[m].p, q = (p + 1 == N) ? 0 : p + 1, w = cd[m].w, t = cd[m].t;
+            const u64 bit = 1ull << t;
+            bool spawn, changed;
+            const bool stopped = apply_res(A, C, b, true, p, q, res[m], status, spawn, changed);
+            att[w] &= ~bit;
+            if (stopped) { Lw[w] &= ~bit; live.set_word(w, Lw[w]); --nlive; }
+            if (changed) {
+                if (t < 63) att[w] |= Lw[w] & (bit << 1);
+                else if (w + 1 < NW && (Lw[w + 1] & 1ull)) { att[w + 1] |= 1ull; todo |= 1ull << (w + 1); }
+            }
+            if (!att[w]) todo &= ~(1ull << w); else todo |= 1ull << w;
+        }
+    }
+    for (int w = 0; w < NW; ++w) if (!Lw[w]) words &= ~(1ull << w);
+}
+
 inline void qss_memo_q_proto(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b) {
     const int N = A.N, ld = A.ld;
     const double lat0 = max_lat_acc(V, 0.0);
@@ -314,7 +400,8 @@ inline void qss_memo_q_proto(const QssArgs& A, const MemoWork& W, const MemoCtx&
         int wB = 0, wF = 0, deadB = 0, deadF = 0;
         if (nB > 0) wB = memo_spawned_rows_q<false>(A, W, C, V, b, false, s, lat0, nB, nB, nnew, steps, status, PB, deadB);
         if (iters == 0 && nliveF == N) memo_forward_sweep0(A, W, C, V, b, lat0, nliveF, steps, status);
-        memo_original_rows<true>(A, W, C, V, b, nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status);
+        if (g_mq_fpar) memo_forward_rows_par(A, W, C, V, b, nliveF == 0, s, lat0, nliveF, wordsF, steps, status);
+        else memo_original_rows<true>(A, W, C, V, b, nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status);
         if (nF > 0) wF = memo_spawned_rows_q<true>(A, W, C, V, b, false, s, lat0, nF, nB, none, steps, status, PB, deadF);
         if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
         for (int j = 0; j < nnew; ++j) {

@@ -179,6 +179,55 @@ def test_qss_memo_random_tracks(sto):
             assert float(res["lap"][c]) == o["lap"] and float(res["summary"][6, c]) == o["steps"], (n, c)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+def test_qss_kernel_variants_equal_oracle(sto, kernel):
+    """The selectable small-batch kernels (tuning key qss_kernel): 1 the four-walker lane-group kernel, 2 the one-loop
+    kernel with the sequential forward sweep, 3 the one-loop kernel with the re-spawned lists walked out of order
+    (sto_qss_memo3.cuh), 4 = default, the one-loop kernel with the forward original-row sub-pass run-parallel.  Random tracks
+    (8 different lines per warp), word-boundary sizes, 16 / 32-lane groups and 64 lines of the golden Monza line with
+    perturbed radii (4 x 8 lanes): speeds, segment times, laps, front-step and iteration counts equal the oracle's."""
+    from helpers import synthetic_closed_track
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    d = golden("sim_s10k3_i2")
+    veh, ov = _lib.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    n_full = len(d["in_X"])
+    batches = []
+    for n in (200, 640):
+        T = [synthetic_closed_track(77000 + 10 * n + c, n) for c in range(8)]
+        batches.append(tuple(np.stack([t[k] for t in T]) for k in range(3)) + (T[0][3], 0))
+    for n in (129, 193, 1025):
+        X, Y, R = np.empty((8, n)), np.empty((8, n)), np.empty((8, n))
+        for c in range(8):
+            idx = (np.linspace(0, n_full - 1, n, endpoint=False).astype(int) + 53 * c) % n_full
+            X[c], Y[c], R[c] = d["in_X"][idx], d["in_Y"][idx], d["in_CURVATURE"][idx] * (1.0 + 0.02 * c)
+        batches.append((X, Y, R, np.zeros(n), 0))
+    B = 64
+    X = np.tile(d["in_X"], (B, 1)); Y = np.tile(d["in_Y"], (B, 1))
+    R = d["in_CURVATURE"][None, :] * (1.0 + 0.004 * np.arange(B))[:, None]
+    batches.append((X, Y, R, np.sin(d["in_BANK"]), 8))       # forced 4 lines x 8 lanes per warp
+    batches.append((X[:6], Y[:6], R[:6], np.sin(d["in_BANK"]), 16))
+    try:
+        _lib.check(lib.sto_set_tuning(b"qss_kernel", kernel))
+        for X, Y, R, sb, group in batches:
+            _lib.check(lib.sto_set_tuning(b"qss_group", group))
+            nb = X.shape[0]
+            res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=nb, sin_bank=sb, impl=sto.IMPL["memo"])
+            torch.cuda.synchronize()
+            assert not res["status"][:nb].cpu().numpy().any()
+            for c in range(0, nb, 1 if nb <= 8 else 9):
+                o = O.qss(X[c], Y[c], R[c], sb, ov, 0)
+                assert np.array_equal(res["speed"][:, c].cpu().numpy(), o["v"]), (kernel, X.shape, c)
+                assert np.array_equal(res["lon_acc"][:, c].cpu().numpy(), o["a"]), (kernel, X.shape, c)
+                assert np.array_equal(res["time"][:, c].cpu().numpy(), o["time"]), (kernel, X.shape, c)
+                assert float(res["lap"][c]) == o["lap"], (kernel, X.shape, c)
+                assert float(res["summary"][6, c]) == o["steps"] and float(res["summary"][7, c]) == o["iters"] + 1
+    finally:
+        _lib.check(lib.sto_set_tuning(b"qss_kernel", 0))
+        _lib.check(lib.sto_set_tuning(b"qss_group", 0))
+
+
 @pytest.mark.parametrize("impl", ["plain", "memo"])
 def test_qss_synthetic_tables(sto, impl):
     """Infinite turn radius, banked samples, N = 8 / 64 / 257 (tiny N runs the plain kernel under 'memo')."""

@@ -94,6 +94,7 @@ def test_qss_lane_group_emulation_bit_exact(name, group):
     for k in ("v", "a", "lat", "time"):
         assert np.array_equal(r[k][0], o[k]), k
     assert r["lap"][0] == o["lap"] and r["summary"][0, 6] == o["steps"]
+    assert r["summary"][0, 7] == o["iters"] + 1     # (a trailing tombstone in the backward list must not cost an iteration)
 
 
 @pytest.mark.parametrize("n", [128, 129, 191, 192, 193, 256, 257, 321, 1024, 1025])
@@ -130,7 +131,7 @@ def test_qss_memo_random_tracks(seed):
         assert h["status"][0] == 0
         for k in ("v", "a", "lat", "time"):
             assert np.array_equal(h[k][0], o[k]), (impl, k)
-        assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"]
+        assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1, impl
 
 
 def test_forward_list_batch_prototype_is_exact():
@@ -402,3 +403,48 @@ def test_out_of_order_list_walk_model_is_exact(lanes):
         assert h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1, case
         for k in ("v", "a"):
             assert np.array_equal(h[k][0], o[k], equal_nan=True), (case, k)
+
+
+def test_parallel_forward_rows_model_is_exact():
+    """Host model (tests/hostsim/memo3_proto.h, memo_forward_rows_par) of the run-parallel forward sub-pass over the original
+    rows that the lane-group kernel offers (sto_qss_memo2.cuh, FP): per round the lowest words with dirty fronts each offer
+    their lowest dirty front if no dirty front sits below it in its run of consecutive live rows; all are evaluated on the
+    state as it stands and committed together.  Must equal the oracle bit for bit; reports rounds against evaluations."""
+    import ctypes as C
+    from helpers import synthetic_closed_track, nan_cases
+    L = H.lib()
+    L.hostsim_mq_config(32, 8, 1)
+    L.hostsim_mf_config(1)
+    out = (C.c_longlong * 3)()
+    try:
+        d = golden("sim_s10k3_i2")
+        ov, hv = O.make_vehicle(*veh_args(d)), H.make_vehicle(*veh_args(d))
+        cases = []
+        for name in ("sim_s10k3_i2", "sim_s30k5_i3", "sim_oval_bank12", "sim_s10k3_i5"):
+            g = golden(name)
+            cases.append((g["in_X"], g["in_Y"], g["in_CURVATURE"], np.sin(g["in_BANK"])))
+        for seed in range(10):
+            n = int(np.random.default_rng(1900 + seed).integers(128, 1500))
+            cases.append(synthetic_closed_track(4000 + seed, n))
+        for n in (128, 129, 192, 193, 257):
+            idx = np.linspace(0, len(d["in_X"]) - 1, n, endpoint=False).astype(int)
+            cases.append((d["in_X"][idx].copy(), d["in_Y"][idx].copy(), d["in_CURVATURE"][idx].copy(), np.zeros(n)))
+        L.hostsim_mf_stats(out, 1)
+        for x, y, r, sb in cases:
+            o = O.qss(x, y, r, sb, ov, 0)
+            h = H.qss(301, x[None], y[None], r[None], sb, hv)
+            assert h["status"][0] == 0
+            for k in ("v", "a", "lat", "time"):
+                assert np.array_equal(h[k][0], o[k]), k
+            assert h["lap"][0] == o["lap"] and h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1
+        L.hostsim_mf_stats(out, 1)
+        assert out[1] > 2 * out[0] > 0          # more than two evaluations per round
+        for case, (x, y, r, sb) in nan_cases().items():
+            o = O.qss(x, y, r, sb, ov, 0)
+            h = H.qss(301, x[None], y[None], r[None], sb, hv)
+            assert h["status"][0] == 2, case
+            assert h["summary"][0, 6] == o["steps"] and h["summary"][0, 7] == o["iters"] + 1, case
+            for k in ("v", "a"):
+                assert np.array_equal(h[k][0], o[k], equal_nan=True), (case, k)
+    finally:
+        L.hostsim_mf_config(0)

@@ -13,16 +13,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from spline_trajectory_optimization_b200 import _lib, build  # noqa: E402
 
-alt = os.path.join(ROOT, "gpurun_out", "libsto_b200_phase.so")
+# built here (the authoring container cross-compiles; `--build-only`) and shipped to the GPU box with the tree
+alt = os.path.join(ROOT, "ab", "libsto_b200_phase.so")
 os.makedirs(os.path.dirname(alt), exist_ok=True)
-cmd = [build.nvcc_path()] + [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DSTO_PHASE_CLOCKS", "-o", alt,
-       os.path.join(build.CSRC, "sto_b200.cu")]
-subprocess.check_call(cmd)
+if "--build-only" in sys.argv or not os.path.exists(alt):
+    cmd = [build.nvcc_path()] + [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DSTO_PHASE_CLOCKS", "-o", alt,
+           os.path.join(build.CSRC, "sto_b200.cu")]
+    subprocess.check_call(cmd)
+    if "--build-only" in sys.argv:
+        sys.exit(0)
 _lib.LIB_PATH = alt
 import bench  # noqa: E402
 from spline_trajectory_optimization_b200.evaluator import BatchedLineEvaluator, run_qss  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4096
 rt, veh = bench.build_track(), bench.test_vehicle()
 ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(), veh, impl="memo")
 off = ev.to_sample_major(torch.from_numpy(bench.make_offsets(rt, B, 1234)).cuda())
@@ -66,3 +70,8 @@ else:
     for k, n in enumerate(names3):
         print("%-46s mean %.3g  max %.3g clocks  (%.2f / %.2f ms)" % (n, oth[k].mean(), oth[k].max(), oth[k].mean() / 1.965e6, oth[k].max() / 1.965e6))
     print("round loop, max over candidates: %.2f ms" % (allv[:12].sum(axis=0).max() / 1.965e6))
+    if int(os.environ.get("STO_QSS_KERNEL", "0")) == 3:
+        c4 = res["lon_acc"][:8, :B].cpu().numpy().mean(axis=1)
+        print("list phases (sto_qss_memo3.cuh): scan %.3g clocks in %.0f steps (%.0f per step), selection %.3g clocks in %.0f passes "
+              "(%.0f per pass), chunk end %.3g clocks for %.0f chunks (%.0f per chunk)" % (
+                  c4[0], c4[1], c4[0] / max(c4[1], 1), c4[2], c4[3], c4[2] / max(c4[3], 1), c4[4], c4[5], c4[4] / max(c4[5], 1)))
