@@ -293,6 +293,7 @@ inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCt
 // committed together; a changing step makes the next live row dirty.
 struct MemoFStats { long long rounds = 0, evals = 0, subpasses = 0; };
 static MemoFStats g_mf;
+static int g_mf_allruns = 0;
 
 inline void memo_forward_rows_par(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
                                   bool skip, int s, double lat0, int& nlive, u64& words, int64_t& steps, int& status) {
@@ -318,6 +319,26 @@ inline void memo_forward_rows_par(const QssArgs& A, const MemoWork& W, const Mem
         Cd cd[64];
         int nc = 0;
         u64 tw = todo;
+        if (g_mf_allruns) {
+            // every run of consecutive live rows offers its lowest dirty front (several per word), lowest rows first
+            bool below_dirty = false;   // a dirty front sits below in the current run
+            for (int w = 0; w < NW && nc < G; ++w) {
+                const int nbits = (N - 64 * w >= 64) ? 64 : N - 64 * w;
+                if (!att[w] && Lw[w] == ((nbits == 64) ? ~0ull : ((1ull << nbits) - 1ull))) continue;   // fully live, clean: run goes on
+                for (int t = 0; t < nbits && nc < G; ++t) {
+                    const u64 bit = 1ull << t;
+                    if (!(Lw[w] & bit)) { below_dirty = false; continue; }
+                    if (!(att[w] & bit)) continue;
+                    if (below_dirty) continue;
+                    int p = 64 * w + t + s;
+                    if (p >= N) p -= N;
+                    if (stop.test(p)) { Lw[w] &= ~bit; live.set_word(w, Lw[w]); --nlive; att[w] &= ~bit; below_dirty = false; continue; }
+                    cd[nc++] = Cd{w, t, p};
+                    below_dirty = true;
+                }
+                if (!att[w]) todo &= ~(1ull << w);
+            }
+        } else
         for (int g = 0; g < G && tw; ++g) {
             const int w = ctz64(tw);
             tw &= tw - 1ull;
@@ -370,6 +391,95 @@ inline void memo_forward_rows_par(const QssArgs& A, const MemoWork& W, const Mem
     for (int w = 0; w < NW; ++w) if (!Lw[w]) words &= ~(1ull << w);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Prototype 4 (analysis / test only): a re-spawned list processed by RUNS OF ROWS.  The live entries of a list occupy
+// virtual rows; an entry only affects entries on the next row (forward) / the previous row (backward).  Rows whose edge
+// memo is not CONT are open; a maximal run of occupied adjacent rows is cut at its first open row (in the direction of
+// travel) and everything from there on is a WORK RUN.  Work runs are independent of each other; the entries of one work
+// run are processed one at a time in list order (which IS the reference order restricted to entries that can interact).
+struct MemoRStats { long long walks = 0, runs = 0, evals = 0, rounds_est = 0, longest = 0, entries_in_runs = 0, visits = 0; };
+static MemoRStats g_mr[2];
+static int g_mq_rows = 0;
+
+template <bool FWD>
+inline int memo_spawned_rows_runs(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
+                                  bool skip, int s, double lat0, int nlist, int nB, int& nnew, int64_t& steps, int& status,
+                                  int& ndead) {
+    const int N = A.N, ld = A.ld, d = FWD ? 1 : 0, G = g_mq_lanes;
+    const Ring cont = C.cont(d), stop = C.stop(d);
+    int32_t* list = FWD ? W.spF : W.spB;
+    if (skip) nlist = 0;
+    if (!nlist) return 0;
+    ++g_mr[d].walks;
+    // live entries by virtual row
+    std::vector<std::vector<int>> at_row(N);     // list indices, ascending
+    std::vector<char> occ(N, 0), openr(N, 0), inrun(N, 0);
+    for (int r = 0; r < nlist; ++r) {
+        const int iv = list[at(r, ld, b)];
+        if (iv < 0) continue;
+        ++steps;
+        ++g_mr[d].visits;
+        at_row[iv].push_back(r);
+        occ[iv] = 1;
+    }
+    for (int iv = 0; iv < N; ++iv) {
+        if (!occ[iv]) continue;
+        int p = FWD ? iv + s : iv - s;
+        if (p >= N) p -= N;
+        if (p < 0) p += N;
+        openr[iv] = !cont.test(p);
+    }
+    // work runs: start at an open row whose predecessor row (against the direction of travel) is not in a run
+    auto nextrow = [&](int iv) { return FWD ? ((iv + 1 == N) ? 0 : iv + 1) : ((iv == 0) ? N - 1 : iv - 1); };
+    auto prevrow = [&](int iv) { return FWD ? ((iv == 0) ? N - 1 : iv - 1) : ((iv + 1 == N) ? 0 : iv + 1); };
+    std::vector<std::vector<int>> runs;
+    for (int iv0 = 0; iv0 < N; ++iv0) {
+        if (!openr[iv0] || inrun[iv0]) continue;
+        // walk back: is there an open occupied row connected behind me?  then I belong to its run (found from there)
+        int st = iv0, guard = 0;
+        for (int pv = prevrow(st); occ[pv] && guard < N; pv = prevrow(pv), ++guard) if (openr[pv]) st = pv;
+        if (inrun[st]) continue;
+        std::vector<int> rows;
+        guard = 0;
+        for (int iv = st; occ[iv] && !inrun[iv] && guard < N; iv = nextrow(iv), ++guard) { rows.push_back(iv); inrun[iv] = 1; }
+        runs.push_back(rows);
+    }
+    std::vector<std::pair<int, int>> spawns;   // (list index, q)
+    long long tot = 0, longest = 0;
+    for (const auto& rows : runs) {
+        std::vector<int> ents;
+        for (int iv : rows) for (int r : at_row[iv]) ents.push_back(r);
+        std::sort(ents.begin(), ents.end());
+        g_mr[d].entries_in_runs += (long long)ents.size();
+        long long ne = 0;
+        for (int r : ents) {
+            if (status != 0) break;
+            const int iv = list[at(r, ld, b)];
+            int p = FWD ? iv + s : iv - s;
+            if (p >= N) p -= N;
+            if (p < 0) p += N;
+            if (cont.test(p)) continue;
+            if (stop.test(p)) { list[at(r, ld, b)] = -1; ++ndead; continue; }
+            const int q = FWD ? ((p + 1 == N) ? 0 : p + 1) : ((p == 0) ? N - 1 : p - 1);
+            bool spawn, changed;
+            const bool stopped = memo_step(A, C, V, b, FWD, p, q, lat0, status, spawn, changed);
+            ++ne;
+            if (spawn) spawns.push_back(std::make_pair(r, q));
+            if (stopped) { list[at(r, ld, b)] = -1; ++ndead; }
+        }
+        tot += ne;
+        if (ne > longest) longest = ne;
+    }
+    g_mr[d].runs += (long long)runs.size();
+    g_mr[d].evals += tot;
+    g_mr[d].rounds_est += std::max(longest, (tot + G - 1) / G);
+    g_mr[d].longest = std::max(g_mr[d].longest, longest);
+    std::sort(spawns.begin(), spawns.end());     // new rows in list order of their spawners
+    for (const auto& sp : spawns) { memo_spawn(A, W, b, sp.second, s, nB, nnew, status); ++nnew; }
+    return nlist;   // (no compaction: tombstones stay; the model's caller compacts)
+}
+
 inline void qss_memo_q_proto(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b) {
     const int N = A.N, ld = A.ld;
     const double lat0 = max_lat_acc(V, 0.0);
@@ -398,10 +508,23 @@ inline void qss_memo_q_proto(const QssArgs& A, const MemoWork& W, const MemoCtx&
         int nnew = 0, none = 0;
         memo_original_rows<false>(A, W, C, V, b, nliveB == 0, s, lat0, nB, nnew, nliveB, wordsB, steps, status);
         int wB = 0, wF = 0, deadB = 0, deadF = 0;
+        auto compact = [&](int32_t* list, int n) { int w2 = 0; for (int r2 = 0; r2 < n; ++r2) { const int iv = list[at(r2, ld, b)]; if (iv >= 0) list[at(w2++, ld, b)] = iv; } return w2; };
+        if (nB > 0 && g_mq_rows) {
+            // (the spawned rows sit behind the list: keep them there while compacting)
+            std::vector<int32_t> tail;
+            memo_spawned_rows_runs<false>(A, W, C, V, b, false, s, lat0, nB, nB, nnew, steps, status, deadB);
+            for (int j = 0; j < nnew; ++j) tail.push_back(W.spB[at(nB + j, ld, b)]);
+            wB = compact(W.spB, nB); deadB = 0;
+            for (int j = 0; j < nnew; ++j) W.spB[at(nB + j, ld, b)] = tail[j];
+        } else
         if (nB > 0) wB = memo_spawned_rows_q<false>(A, W, C, V, b, false, s, lat0, nB, nB, nnew, steps, status, PB, deadB);
         if (iters == 0 && nliveF == N) memo_forward_sweep0(A, W, C, V, b, lat0, nliveF, steps, status);
         if (g_mq_fpar) memo_forward_rows_par(A, W, C, V, b, nliveF == 0, s, lat0, nliveF, wordsF, steps, status);
         else memo_original_rows<true>(A, W, C, V, b, nliveF == 0, s, lat0, nB, none, nliveF, wordsF, steps, status);
+        if (nF > 0 && g_mq_rows) {
+            memo_spawned_rows_runs<true>(A, W, C, V, b, false, s, lat0, nF, nB, none, steps, status, deadF);
+            wF = compact(W.spF, nF); deadF = 0;
+        } else
         if (nF > 0) wF = memo_spawned_rows_q<true>(A, W, C, V, b, false, s, lat0, nF, nB, none, steps, status, PB, deadF);
         if (wF + nnew > A.cap) { status |= STO_CAND_ROW_OVERFLOW; nnew = 0; }
         for (int j = 0; j < nnew; ++j) {
