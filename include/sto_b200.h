@@ -92,7 +92,9 @@ int sto_release(void);                /* frees the per-device arenas / streams c
 /* Developer tuning overrides, 0 = automatic: "fit_split" (lanes per candidate of the fit kernels), "qss_lanes" (candidates
  * per warp), "qss_group" (lanes per candidate of the memoised QSS kernel) - powers of two <= 32 - and "qss_planes" (1 bit
  * planes in shared memory, 2 global, 3 all global, 4 CONT planes shared + rest global), "qss_kernel" (small batches: 1 the
- * four-walker kernel, 2 the one-loop kernel, csrc/sto_qss_memo2.cuh; STO_QSS_KERNEL).  The same values are read ONCE
+ * four-walker kernel, 2 the one-loop kernel with the sequential forward sweep, csrc/sto_qss_memo2.cuh, 3 the one-loop
+ * kernel with the re-spawned lists walked out of order, csrc/sto_qss_memo3.cuh, 4 = 0 = the one-loop kernel with the
+ * run-parallel forward sub-pass; STO_QSS_KERNEL).  The same values are read ONCE
  * from the environment (STO_FIT_SPLIT, STO_QSS_LANES, STO_QSS_GROUP, STO_QSS_PLANES, STO_FIT_SOLVER) when the library is
  * loaded; nothing consults the environment afterwards.  Results never depend on these, only speed. */
 int sto_set_tuning(const char* key, int value);
