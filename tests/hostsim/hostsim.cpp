@@ -210,7 +210,7 @@ void hostsim_m3_stats(long long* out9, int reset) {
 void hostsim_mq_config(int cap, int lanes, int war) { sto::g_mq_cap = cap; sto::g_mq_lanes = lanes; sto::g_mq_war = war; }
 void hostsim_mf_config(int on) { sto::g_mq_fpar = on ? 1 : 0; sto::g_mf_allruns = on == 2; }
 void hostsim_mf_stats(long long* out3, int reset) { out3[0] = sto::g_mf.rounds; out3[1] = sto::g_mf.evals; out3[2] = sto::g_mf.subpasses; if (reset) sto::g_mf = sto::MemoFStats(); }
-void hostsim_mr_config(int on) { sto::g_mq_rows = on; }
+void hostsim_mr_config(int on) { sto::g_mq_rows = on == 1; sto::g_mq_wr = on == 2; }
 void hostsim_mr_stats(long long* out14, int reset) { for (int d = 0; d < 2; ++d) { const sto::MemoRStats& m = sto::g_mr[d]; long long v[7] = {m.walks, m.runs, m.evals, m.rounds_est, m.longest, m.entries_in_runs, m.visits}; for (int k = 0; k < 7; ++k) out14[7 * d + k] = v[k]; if (reset) sto::g_mr[d] = sto::MemoRStats(); } }
 void hostsim_mq_stats(long long* out14, int reset) {
     for (int d = 0; d < 2; ++d) {

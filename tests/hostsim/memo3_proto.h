@@ -171,7 +171,7 @@ inline void qss_memo3_proto(const QssArgs& A, const sto_vehicle_f64& V, int b) {
 struct MemoQStats { long long eval_rounds[2] = {0, 0}, idle_rounds[2] = {0, 0}, evals[2] = {0, 0}, chunks[2] = {0, 0},
                     qsum[2] = {0, 0}, visits[2] = {0, 0}, walks[2] = {0, 0}; };
 static MemoQStats g_mq;
-static int g_mq_cap = 32, g_mq_lanes = 8, g_mq_war = 1, g_mq_fpar = 0;
+static int g_mq_cap = 32, g_mq_lanes = 8, g_mq_war = 1, g_mq_fpar = 0, g_mq_wr = 0;
 
 template <bool FWD>
 inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCtx& C, const sto_vehicle_f64& V, int b,
@@ -183,6 +183,23 @@ inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCt
     if (skip) nlist = 0;
     if (nlist) ++g_mq.walks[d];
     int r = 0, w = 0;
+    // g_mq_wr: open entries = entries on WORK-RUN rows (rows of live entries from the first row of a run of occupied adjacent
+    // rows whose edge memo is not CONT, in the direction of travel); everything else is kept without a memo test
+    std::vector<char> WR;
+    if (g_mq_wr && nlist) {
+        std::vector<char> occ(N, 0);
+        WR.assign(N, 0);
+        for (int k = 0; k < nlist; ++k) { const int iv = list[at(k, ld, b)]; if (iv >= 0) occ[iv] = 1; }
+        for (int iv0 = 0; iv0 < N; ++iv0) {
+            if (!occ[iv0] || WR[iv0]) continue;
+            int p0 = FWD ? iv0 + s : iv0 - s;
+            if (p0 >= N) p0 -= N;
+            if (p0 < 0) p0 += N;
+            if (cont.test(p0)) continue;
+            int guard = 0;
+            for (int iv = iv0; occ[iv] && !WR[iv] && guard < N; iv = FWD ? ((iv + 1 == N) ? 0 : iv + 1) : ((iv == 0) ? N - 1 : iv - 1), ++guard) WR[iv] = 1;
+        }
+    }
     int qp[64], qslot[64], qiv[64];
     unsigned long long dep[64], war[64];
     int dead = 0;
@@ -202,6 +219,9 @@ inline int memo_spawned_rows_q(const QssArgs& A, const MemoWork& W, const MemoCt
                 if (p >= N) p -= N;
                 if (p < 0) p += N;
                 const bool c0 = cont.test(p), s0 = stop.test(p);
+                if (g_mq_wr) {
+                    if (!WR[iv]) { list[at(w, ld, b)] = iv; ++w; continue; }
+                } else
                 if ((c0 || s0) && !PB[p]) { if (c0) { list[at(w, ld, b)] = iv; ++w; } continue; }
                 list[at(w, ld, b)] = iv;
                 qslot[nq] = w; ++w;
