@@ -17,9 +17,11 @@
 //
 // A lane group (G lanes) runs one candidate; cpw = 32 / G candidates share a warp and move through (iteration, phase,
 // round) together.  Batch phases (0: backward original rows, 1: backward re-spawned list) give every lane of the group its
-// own front (the backward sub-pass is a Jacobi step); single phases (2, 3: the forward sub-pass is a sequential sweep)
-// evaluate one front per round on all lanes redundantly and lane 0 of the group commits.  The re-spawned lists are
-// candidate-major here ([b][cap]: the G entries at the cursor are one 32-byte sector) and read directly, one chunk ahead.
+// own front (the backward sub-pass is a Jacobi step).  The forward sub-pass is a sequential sweep: phase 3 (the forward
+// re-spawned list) evaluates one front per round on all lanes redundantly; phase 2 (the forward original rows) does the
+// same in the <FP = false> build, and in the default <FP = true> build runs the independent runs of live rows in parallel
+// (see qss_memo2_candidate).  The re-spawned lists are candidate-major here ([b][cap]: the G entries at the cursor are one
+// 32-byte sector) and read directly, one chunk ahead.
 // Tracks of more than 4,096 samples (more than 64 plane words) and the one-lane-per-candidate kernels for large batches
 // stay with sto_qss_memo.cuh.
 #pragma once

@@ -22,6 +22,12 @@
 // tests/test_hostsim.py::test_out_of_order_list_walk_model_is_exact.  Measured on the Monza batch (host model, one line):
 // forward list 5,351 evaluations in ~1,790 rounds, backward list 4,196 in ~650.
 // Entries that stop leave a tombstone (-1) in their reserved slot; the next walk drops it.
+//
+// STATUS: an experiment, selectable (tuning key qss_kernel = 3), NOT the default.  On the device it is bit-exact (every GPU
+// parity test passes with it) and the forward list needs 1,882 rounds per 4-line warp instead of 5,244 - but the scan that
+// classifies the ~44 k list entries a line visits costs 2,064 clocks per 8-entry step (21 M clocks per line) against the
+// ~14 M the saved rounds are worth: 40.2 ms against 33.4 ms at 4,096 lines (profiles/r02b_*lists_out_of_order.txt).  The
+// rounds are there to be had; it is the list scan that has to go (lists by runs of rows).
 #pragma once
 #include "sto_qss_memo2.cuh"
 
