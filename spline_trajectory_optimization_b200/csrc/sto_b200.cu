@@ -615,10 +615,14 @@ int launch_qss(const sto::QssArgs& A, const QssWork& w, const sto_vehicle_f64* v
             const int lanes = pick_lanes(A.B, 0);
             const int warps = (A.B + lanes - 1) / lanes;
             const size_t mixed_smem = (size_t)2 * w.memo.W * 32 * sizeof(unsigned long long) + STO_LIST_RING * 32 * sizeof(int32_t);
-            // mixed placement while every warp of the batch stays resident with its CONT planes in shared memory
-            // (measured: 32,768 candidates 168 ms mixed vs 184 ms all-global; 131,072 candidates 662 vs 559 ms)
+            // mixed placement while the warps of TWO such launches stay resident with their CONT planes in shared memory.
+            // Measured on B200, Monza: one launch of 32,768 candidates 154 ms mixed vs 164 ms all-global (131,072: 662 vs
+            // 559 ms) - but 32,768 candidates are only 7 warps per SM, a caller that keeps two launches in flight (steps
+            // pipelined over two streams, two host threads on the *_host entry) fills the other half of the SM only if the
+            // 25.6 KB of shared memory per warp do not stand in the way: 124.6 ms per step all-global against 156.2 ms
+            // mixed (263 k vs 210 k candidates/s).  So the mixed kernel is left to launches of at most half the SMs' capacity.
             const int resident = 148 * (int)((size_t)227 * 1024 / (mixed_smem + 1024));
-            const bool mixed = (pl >= 3) ? (pl == 4) : (warps <= resident);
+            const bool mixed = (pl >= 3) ? (pl == 4) : (2 * warps <= resident);
             if (mixed && mixed_smem <= kMemoSmemBudget / 4) {
                 STO_CUDA(cudaFuncSetAttribute(qss_memo_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)mixed_smem));

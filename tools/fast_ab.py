@@ -17,7 +17,7 @@ ev = BatchedLineEvaluator(rt.center_d[:, :2], rt.left_normals(), rt.center_d.ts(
 res = []
 for B in (4096, 131072):
     d = candidates.smooth_offsets_device(ev.M, 0, B, rt.dist_to_left, rt.dist_to_right, ev.device, seed=77)
-    for kw in (dict(stage_tables=0), dict(stage_tables=1), dict(stage_tables=0, outputs=True)):
+    for kw in (dict(stage_tables=0), dict(stage_tables=0, outputs=True)):
         r = ev.lap_times_fast(d, B=B, rounds=2, **kw)
         if kw.get("outputs"):
             kw["outputs"] = r[2]
