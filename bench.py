@@ -724,8 +724,32 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         line["large_batch"] = {"candidates_per_step": BL, "value": 2 * BL / (t0e.elapsed_time(t1e) * 1e-3), "unit": UNIT,
                                "ms_per_step": t0e.elapsed_time(t1e) / 2, "all_status_ok": bool((s_l == 0).all().item()),
-                               "note": "262,144 / 8 candidates in one launch; bit planes move to global memory at this "
-                                       "size (DESIGN.md section 2)"}
+                               "note": "262,144 / 8 candidates in one launch, one launch at a time; bit planes in global "
+                                       "memory at this size (DESIGN.md section 2)"}
+        if n_slots > 1:
+            # the same launches with two in flight (one per stream, own workspace each), as the timed steps above run:
+            # 32,768 candidates put 7 warps on an SM, a second launch fills the rest
+            cur = torch.cuda.current_stream(dev)
+            for S in slots[:2]:
+                with torch.cuda.stream(S.stream):
+                    S.ev.lap_times(d_l, B=BL)
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record(cur)
+            n_l = 4
+            for S in slots[:2]:
+                S.stream.wait_event(t0e)
+            for j in range(n_l):
+                S = slots[j % 2]
+                with torch.cuda.stream(S.stream):
+                    l_l, s_l = S.ev.lap_times(d_l, B=BL)
+            for S in slots[:2]:
+                cur.wait_stream(S.stream)
+            t1e.record(cur)
+            torch.cuda.synchronize()
+            line["large_batch"]["pipelined"] = {"value": n_l * BL / (t0e.elapsed_time(t1e) * 1e-3), "unit": UNIT,
+                                                "ms_per_step": t0e.elapsed_time(t1e) / n_l, "launches_in_flight": 2,
+                                                "all_status_ok": bool((s_l == 0).all().item())}
         del d_l
     if args.large_batch and world == 1 and cfg == 1:
         # ---- informational: BASELINE configs[2] (262,144 candidates) on ONE GPU, the strong-scaling reference of the
