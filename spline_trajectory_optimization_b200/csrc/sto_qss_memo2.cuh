@@ -299,7 +299,9 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                         const Sweep0Out o = memo2_sweep0(A, V, rec, P, lat0, nliveF, steps, status);
                         nliveF = o.nlive; status = o.status; steps = o.steps;
                     }
-                    skip = done || nliveF == 0;
+                    // (FP: a candidate that failed in this iteration's backward phases may have left marks in the BLOCKED
+                    //  plane, which this phase reads as attention words: it sits the phase out - its result is NaN anyway)
+                    skip = done || nliveF == 0 || (FP && status != 0);
                     todo = memo2_scan_words<G, FP>(P, true, skip, s, g, wordsF, steps);
                     open = false;
                     if (FP) {
@@ -449,7 +451,11 @@ __device__ void qss_memo2_candidate(const QssArgs& A, const MemoWork& W, const M
                 // forward sub-pass over the original rows, independent live runs in parallel: lane g takes the g-th lowest
                 // word with dirty fronts and offers its lowest dirty front if no dirty front sits below it in its run
                 int nk = 0;
-                for (;;) {
+                for (int look = 0;; ++look) {
+                    if (look > 4 * 64 + 8 && !skip && Tw != 0ull) {   // cannot happen (every look settles a front); never spin
+                        status |= STO_CAND_NO_CONVERGENCE;
+                        skip = true;
+                    }
                     const u64 tw = skip ? 0ull : Tw;
                     if (g < popc64(tw)) {
                         w = kth_bit(tw, g);

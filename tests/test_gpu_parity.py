@@ -687,6 +687,41 @@ def test_status_flags_and_chunked_host_path(sto):
     assert np.array_equal(lap_one[:8], lap_one[88:])
 
 
+@pytest.mark.parametrize("kernel", [2, 3, 4])
+def test_failed_line_shares_a_warp_with_healthy_lines(sto, kernel):
+    """Zero-radius samples (zero initial speed -> the reference's division by zero, status ZERO_SPEED) at different places of
+    some lines of a batch that is forced onto 4 lines x 8 lanes per warp: the failing lines stop with their status bit and a
+    NaN lap at whatever phase of the round loop they fail in, the launch terminates, and the healthy lines of the same warps
+    equal the oracle bit for bit (laps, speeds, step and iteration counts)."""
+    from spline_trajectory_optimization_b200 import _lib
+    lib = _lib.load()
+    d = golden("cand_m579_n579")
+    veh, ov = _lib.make_vehicle(*veh_args(d)), O.make_vehicle(*veh_args(d))
+    B = 16
+    X, Y, R = (np.tile(d[k][:8], (2, 1)).copy() for k in ("ref_X", "ref_Y", "ref_CURVATURE"))
+    R *= (1.0 + 0.01 * np.arange(B))[:, None]
+    bad = {1: [100], 6: [3, 250, 251, 400], 9: [578], 15: [0, 1, 2]}
+    for c, where in bad.items():
+        R[c, where] = 0.0
+    try:
+        _lib.check(lib.sto_set_tuning(b"qss_kernel", kernel))
+        _lib.check(lib.sto_set_tuning(b"qss_group", 8))
+        res = sto.run_qss(to_sm(X), to_sm(Y), to_sm(R), veh, B=B, impl=sto.IMPL["memo"])
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.sto_set_tuning(b"qss_kernel", 0))
+        _lib.check(lib.sto_set_tuning(b"qss_group", 0))
+    st, lap = res["status"][:B].cpu().numpy(), res["lap"][:B].cpu().numpy()
+    for c in range(B):
+        if c in bad:
+            assert st[c] & _lib.CAND_ZERO_SPEED and np.isnan(lap[c]), c
+            continue
+        o = O.qss(X[c], Y[c], R[c], np.zeros(X.shape[1]), ov, 0)
+        assert st[c] == 0 and lap[c] == o["lap"], c
+        assert np.array_equal(res["speed"][:, c].cpu().numpy(), o["v"]), c
+        assert float(res["summary"][6, c]) == o["steps"] and float(res["summary"][7, c]) == o["iters"] + 1, c
+
+
 @pytest.mark.parametrize("case", ["nan_radius", "nan_position", "all_nan", "nan_mixed"])
 def test_qss_nan_inputs_equal_oracle(sto, case):
     """NaN inside a live line: the reference's spawn test (simulator.py:239, `g > max_curve_speed or g < min_state_speed`)
